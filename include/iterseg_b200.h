@@ -1,0 +1,155 @@
+/* iterseg_b200 -- C-ABI of the B200-native affinity U-Net watershed path.
+ *
+ * The reference (AbigailMcGovern/iterseg) is pure Python; its "FFI" for this
+ * path is the Python plug-in protocol of src/iterseg/segmentation.py,
+ * predict.py and watershed.py.  Every entry point below replaces the body of
+ * one of those functions; the Python host (iterseg_b200/*.py) keeps the
+ * reference names/signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types.
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - no allocation inside compute calls: the caller provides a workspace whose
+ *     size comes from the matching *_workspace_bytes() query.
+ *   - return 0 on success, non-zero on failure; isg_last_error() gives the text.
+ *   - volumes are C-contiguous zyx; "padded" means one zero voxel on every face,
+ *     i.e. shape (Z+2, Y+2, X+2), exactly as segmentation.py:890-895 allocates.
+ */
+#ifndef ITERSEG_B200_H
+#define ITERSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISG_OK 0
+#define ISG_ERR_CUDA 1
+#define ISG_ERR_ARG 2
+#define ISG_ERR_WORKSPACE 3
+#define ISG_ERR_OVERFLOW 4
+#define ISG_ERR_DEVICE 5
+
+/* ---- library ------------------------------------------------------------ */
+int isg_version(void);
+const char *isg_last_error(void);
+/* 0 iff a CUDA device of compute capability 10.x is current. */
+int isg_device_check(void);
+/* how many kernels this library has launched since load (bench `gpu_launches`) */
+uint64_t isg_launch_count(void);
+
+/* ---- affinity flood ------------------------------------------------------
+ * Replaces raveled_affinity_watershed (watershed.py:95-159) together with the
+ * data preparation of _prep_data (watershed.py:38-63).
+ *
+ *   aff        3 affinity planes (z,y,x), float32, plane p at aff + p*aff_plane_stride,
+ *              each of shape (Za,Ya,Xa) = padded shape minus 2*aff_origin per axis:
+ *              aff_origin = 0 -> planes are padded like `labels` (the reference layout,
+ *              watershed.py:196-201); aff_origin = 1 -> planes are the unpadded U-Net
+ *              channels and the zero border is implicit.
+ *   aff_div    3 floats on the device: every key is IEEE fp32 aff / aff_div[axis]
+ *              (the per-channel max normalisation of watershed.py:195); pass ones
+ *              for already normalised input.
+ *   mask       (Zp,Yp,Xp) uint8, non-zero = flood may spread here; faces must be 0.
+ *   seeds      n_seeds flat indices into the padded volume, in label order
+ *              (label i+1 for seeds[i], watershed.py:61-62).
+ *   aff_scale_host  3 host floats or NULL: keys are additionally multiplied by |scale|
+ *              (the `scale` argument of affinity_watershed, watershed.py:23-24).
+ *   labels     (Zp,Yp,Xp) uint32, in/out.  Written: seeds[i] -> i+1, then the flood.
+ *              Voxels that are already non-zero on entry are never claimed.
+ * Result: bit-identical to the reference kernel for finite keys.
+ */
+size_t isg_flood_workspace_bytes(int64_t zp, int64_t yp, int64_t xp, int64_t max_seeds);
+int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, int aff_origin,
+                       const float *aff_div, const uint8_t *mask,
+                       const int64_t *seeds, int64_t n_seeds, uint32_t *labels,
+                       int64_t zp, int64_t yp, int64_t xp,
+                       const float *aff_scale_host,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- feature map -> labels ----------------------------------------------
+ * Replaces segment_output_image (watershed.py:165-223) and its helpers
+ * _get_centroids (:232-236), _get_mask (:226-229), _remove_unwanted_objects
+ * (:239-251), affinity_watershed (:17-35).
+ *
+ *   feats            (n_chan, Z, Y, X) float32, channel c at feats + c*Z*Y*X
+ *   aff_ch[3], mask_ch, cent_ch   channel indices (segmentation.py:192-193)
+ *   gauss1_host / gauss2_host     float64 half-kernels w[0..r] of the sigma=1 and
+ *                                 sigma=2 Gaussians (host memory; numpy computes them
+ *                                 exactly as scipy does), radii r1, r2
+ *   peak_thresh      threshold_abs of peak_local_max (0.04, watershed.py:235)
+ *   absolute_thresh  if use_absolute_thresh != 0 the mask is feats[mask_ch] > absolute_thresh
+ *                    (watershed.py:209-212), otherwise Otsu of the sigma=2 smoothed channel
+ *   min_area/max_area  keep components with min_area <= size < max_area (watershed.py:215)
+ *   labels           (Z+2, Y+2, X+2) uint32, must be zero on entry; written in place
+ *   mask_out         (Z+2, Y+2, X+2) uint8: the kept mask (third return value)
+ *   seeds_out        capacity max_seeds flat PADDED indices of the kept seeds, label order
+ *   counts_out       device int64[4]: {n_seeds_kept, n_candidates, n_components, n_multi_seed_components}
+ *   otsu_out         device float[1]: the threshold used
+ */
+typedef struct {
+    int aff_ch[3];
+    int mask_ch;
+    int cent_ch;
+    int r1;
+    int r2;
+    float peak_thresh;
+    int use_absolute_thresh;
+    float absolute_thresh;
+    int64_t min_area;
+    int64_t max_area;
+    float scale[3]; /* |scale| multiplies the affinities (watershed.py:23-24); 1,1,1 = None */
+} isg_post_params;
+
+size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds);
+int isg_segment_features(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
+                         const isg_post_params *params,
+                         const double *gauss1_host, const double *gauss2_host,
+                         uint32_t *labels, uint8_t *mask_out, int64_t *seeds_out,
+                         int64_t max_seeds, int64_t *counts_out, float *otsu_out,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- 3-D U-Net over chunks ----------------------------------------------
+ * Replaces process_chunks + predict_chunk_feature_map + UNet.forward
+ * (predict.py:64-126, unet.py:284-364) for the bundled architecture
+ * UNet(in_channels=1, out_channels=5) with train-mode BatchNorm (per-chunk
+ * statistics), see include comments in iterseg_b200/csrc/unet.cuh.
+ *
+ * Weights: the caller passes the state_dict tensors (device, float32, in the
+ * key order of SURVEY.md Appendix A, running stats and biases of convs may be
+ * NULL: they do not influence train-mode output) through isg_unet_weights_pack,
+ * which writes the packed fp16 tap-major layout into `packed`.
+ */
+typedef struct isg_unet_plan isg_unet_plan;
+
+size_t isg_unet_packed_weight_bytes(void);
+/* tensors: array of 134 device pointers in state_dict order (NULL allowed for
+ * entries that are unused: conv biases, running_mean/var, num_batches_tracked) */
+int isg_unet_weights_pack(const void *const *tensors, int n_tensors, void *packed, void *stream);
+
+size_t isg_unet_workspace_bytes(int n_chunks, int cz, int cy, int cx);
+/* chunk tables are HOST arrays of n_chunks*3 int32: start (z,y,x), crop_lo, crop_hi
+ * exactly as make_chunks returns them (predict.py:38-61). */
+isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n_chunks,
+                                    int cz, int cy, int cx,
+                                    int64_t z, int64_t y, int64_t x,
+                                    const int32_t *starts_host, const int32_t *crop_lo_host,
+                                    const int32_t *crop_hi_host,
+                                    void *workspace, size_t workspace_bytes);
+void isg_unet_plan_destroy(isg_unet_plan *plan);
+/* frame (Z,Y,X) float32 -> feats (5,Z,Y,X) float32: every voxel written by exactly
+ * one chunk's cropped interior (predict.py:89-95). */
+int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream);
+/* debugging / parity: copy an intermediate activation of chunk `chunk` to fp32 NCDHW */
+int isg_unet_debug_activation(isg_unet_plan *plan, const char *name, int chunk, float *out,
+                              int64_t out_elems, void *stream);
+/* algorithmic FLOPs of one forward over all chunks of the plan (2*MAC of 18 conv + 4 tconv) */
+double isg_unet_plan_flops(const isg_unet_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITERSEG_B200_H */

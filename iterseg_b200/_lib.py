@@ -1,0 +1,87 @@
+"""ctypes binding of libiterseg_b200.so (the C-ABI in include/iterseg_b200.h).
+
+There is no CPU fallback: if the library is missing the import of any compute
+entry point raises, and every compute call requires a CUDA device.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libiterseg_b200.so')
+
+_c = ctypes
+_vp, _i64, _i32, _sz, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_size_t, _c.c_float
+
+
+class PostParams(_c.Structure):
+    _fields_ = [('aff_ch', _i32 * 3), ('mask_ch', _i32), ('cent_ch', _i32), ('r1', _i32),
+                ('r2', _i32), ('peak_thresh', _f32), ('use_absolute_thresh', _i32),
+                ('absolute_thresh', _f32), ('min_area', _i64), ('max_area', _i64),
+                ('scale', _f32 * 3)]
+
+
+# name -> (restype, argtypes); this table is also what the symbol-export test checks
+SIGNATURES = {
+    'isg_version': (_i32, []),
+    'isg_last_error': (_c.c_char_p, []),
+    'isg_device_check': (_i32, []),
+    'isg_launch_count': (_c.c_uint64, []),
+    'isg_flood_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
+    'isg_affinity_flood': (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
+                                  _vp, _vp, _sz, _vp]),
+    'isg_post_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
+    'isg_segment_features': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _vp,
+                                    _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    'isg_unet_packed_weight_bytes': (_sz, []),
+    'isg_unet_weights_pack': (_i32, [_vp, _i32, _vp, _vp]),
+    'isg_unet_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32]),
+    'isg_unet_plan_create': (_vp, [_vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
+                                   _vp, _sz]),
+    'isg_unet_plan_destroy': (None, [_vp]),
+    'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),
+    'isg_unet_debug_activation': (_i32, [_vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
+    'isg_unet_plan_flops': (_c.c_double, [_vp]),
+}
+
+_lib = None
+
+
+class IsgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IsgError(
+            f'{LIB_PATH} is missing: build it with `python -m iterseg_b200._build` '
+            '(there is no CPU fallback for this path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().isg_last_error().decode('utf-8', 'replace')
+        raise IsgError(f'{what} failed (status {rc}): {msg}')
+
+
+def require_device():
+    """Raise unless a compute-capability-10.x CUDA device is usable."""
+    import torch
+    if not torch.cuda.is_available():
+        raise IsgError('iterseg_b200 needs a CUDA (sm_100a) device; there is no CPU fallback')
+    check(load().isg_device_check(), 'isg_device_check')
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,39 @@
+// Library-level entry points: version, error text, launch counter.
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace isg {
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+}  // namespace isg
+
+extern "C" int isg_version(void) { return 100; }
+extern "C" const char *isg_last_error(void) { return isg::g_err; }
+extern "C" uint64_t isg_launch_count(void) { return isg::g_launches.load(); }
+extern "C" int isg_device_check(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        isg::set_error("no CUDA device visible");
+        return ISG_ERR_DEVICE;
+    }
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        isg::set_error("device %d has compute capability %d.x; this library is sm_100a only", dev, major);
+        return ISG_ERR_DEVICE;
+    }
+    return ISG_OK;
+}

@@ -1,0 +1,289 @@
+// Host orchestration of the component-wise exact flood + the C-ABI entry
+// isg_affinity_flood (replaces affinity_watershed / _prep_data /
+// raveled_affinity_watershed, src/iterseg/watershed.py:17-159).
+#include <cub/cub.cuh>
+
+#include "flood.cuh"
+
+namespace isg {
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+
+// output[raveled_markers] = 1..N (watershed.py:61-62); duplicates: the last
+// (= largest) label wins, as with numpy fancy assignment.
+__global__ void seed_label_kernel(const int64_t *__restrict__ seeds, int64_t n, uint32_t *labels,
+                                  uint8_t *dom, uint64_t npix) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t s = seeds[i];
+    if (s < 0 || (uint64_t)s >= npix) return;
+    atomicMax(labels + s, (uint32_t)(i + 1));
+    if (dom) dom[s] = 1;
+}
+
+// flood domain of the generic entry point: claimable voxels (in mask and not
+// pre-labelled); seed voxels are added by seed_label_kernel afterwards.
+__global__ void domain_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ labels,
+                              uint8_t *__restrict__ dom, uint64_t n) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        dom[v] = (mask[v] != 0 && labels[v] == 0) ? 1 : 0;
+}
+
+// key = root << 32 | padded flat index, value = label; seeds outside the
+// domain (cannot happen through the public entry points) sort to the end.
+__global__ void seed_key_kernel(const int64_t *__restrict__ seeds, int64_t n,
+                                const uint32_t *__restrict__ n_dev,
+                                const uint32_t *__restrict__ parent, uint64_t npix,
+                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool live = n_dev == nullptr || i < (int64_t)*n_dev;
+    int64_t s = live ? seeds[i] : -1;
+    uint64_t k = ~0ull;
+    if (s >= 0 && (uint64_t)s < npix) {
+        uint32_t r = parent[s];
+        if (r != CCL_NONE) k = ((uint64_t)r << 32) | (uint64_t)s;
+    }
+    keys[i] = k;
+    vals[i] = (uint32_t)(i + 1);
+}
+
+// Single CTA: split the sorted seed list into components, give single-seed
+// components their fill label, multi-seed components a heap arena slice.
+__global__ void __launch_bounds__(1024)
+comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
+                  const uint32_t *__restrict__ comp_size, uint32_t *__restrict__ comp_label,
+                  uint32_t *__restrict__ comp_start, uint64_t *__restrict__ arena_off,
+                  uint32_t *__restrict__ n_comp_out, uint32_t *__restrict__ n_multi_out) {
+    typedef cub::BlockScan<uint32_t, 1024> Scan32;
+    typedef cub::BlockScan<uint64_t, 1024> Scan64;
+    __shared__ union {
+        typename Scan32::TempStorage s32;
+        typename Scan64::TempStorage s64;
+    } tmp;
+    __shared__ uint32_t carry32;
+    __shared__ uint64_t carry64;
+    __shared__ uint32_t multi;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) { carry32 = 0; carry64 = 0; multi = 0; }
+    __syncthreads();
+    // pass 1: component heads
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + t;
+        uint32_t head = 0;
+        if (i < n) {
+            uint64_t k = keys[i];
+            if (k != ~0ull) {
+                uint32_t r = (uint32_t)(k >> 32);
+                head = (i == 0 || (uint32_t)(keys[i - 1] >> 32) != r) ? 1u : 0u;
+            }
+        }
+        uint32_t pos, total;
+        Scan32(tmp.s32).ExclusiveSum(head, pos, total);
+        if (head) comp_start[carry32 + pos] = i;
+        __syncthreads();
+        if (t == 0) carry32 += total;
+        __syncthreads();
+    }
+    const uint32_t n_comp = carry32;
+    // number of valid (in-domain) seeds = first index holding the sentinel
+    if (t == 0) {
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (keys[mid] == ~0ull) hi = mid; else lo = mid + 1;
+        }
+        comp_start[n_comp] = lo;
+        *n_comp_out = n_comp;
+    }
+    __syncthreads();
+    // pass 2: fill labels and arena offsets
+    for (uint32_t base = 0; base < n_comp; base += 1024) {
+        uint32_t c = base + t;
+        uint64_t need = 0;
+        if (c < n_comp) {
+            uint32_t s0 = comp_start[c], s1 = comp_start[c + 1];
+            uint32_t root = (uint32_t)(keys[s0] >> 32);
+            uint32_t cnt = s1 - s0;
+            if (cnt == 1) {
+                comp_label[root] = vals[s0];
+            } else {
+                comp_label[root] = LABEL_MULTI;
+                need = (uint64_t)comp_size[root] + cnt;
+                atomicAdd(&multi, 1u);
+            }
+        }
+        uint64_t pos, total;
+        Scan64(tmp.s64).ExclusiveSum(need, pos, total);
+        if (c < n_comp) arena_off[c] = carry64 + pos;
+        __syncthreads();
+        if (t == 0) carry64 += total;
+        __syncthreads();
+    }
+    if (t == 0) {
+        arena_off[n_comp] = carry64;
+        *n_multi_out = multi;
+    }
+}
+
+// Single-seed components: every claimable voxel takes the seed's label.
+__global__ void __launch_bounds__(256)
+fill_single_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ comp_label,
+                   const uint8_t *__restrict__ mask, uint32_t *__restrict__ labels, uint64_t n) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        uint32_t r = parent[v];
+        if (r == CCL_NONE || !mask[v]) continue;
+        uint32_t cl = comp_label[r];
+        if (cl != 0 && cl != LABEL_MULTI && labels[v] == 0) labels[v] = cl;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage drivers shared by isg_affinity_flood and isg_segment_features
+// ---------------------------------------------------------------------------
+int ccl_run(const uint8_t *dom, uint32_t *parent, uint32_t *comp_size, uint32_t zp, uint32_t yp,
+            uint32_t xp, cudaStream_t st) {
+    const uint64_t npix = (uint64_t)zp * yp * xp;
+    const int grid = num_sms() * 8;
+    ccl_init_kernel<<<grid, 256, 0, st>>>(dom, parent, npix);
+    ISG_LAUNCHED();
+    ccl_union_kernel<<<grid, 256, 0, st>>>(dom, parent, zp, yp, xp);
+    ISG_LAUNCHED();
+    ccl_flatten_count_kernel<<<grid, 256, 0, st>>>(parent, comp_size, npix);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds) {
+    if (max_seeds < 1) max_seeds = 1;
+    b->keys_a = cv.take<uint64_t>(max_seeds);
+    b->keys_b = cv.take<uint64_t>(max_seeds);
+    b->vals_a = cv.take<uint32_t>(max_seeds);
+    b->vals_b = cv.take<uint32_t>(max_seeds);
+    b->comp_start = cv.take<uint32_t>(max_seeds + 1);
+    b->arena_off = cv.take<uint64_t>(max_seeds + 1);
+    b->scalars = cv.take<uint32_t>(64);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_seeds);
+    b->cub_bytes = cub_bytes + 256;
+    b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
+    // heap arena: every domain voxel enters a heap at most once, plus the seeds
+    b->arena_cap = npix + (uint64_t)max_seeds;
+    b->arena_keys = cv.take<uint64_t>(b->arena_cap);
+    b->arena_idx = cv.take<uint32_t>(b->arena_cap);
+    return cv.off;
+}
+
+int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uint8_t *mask,
+                    const uint32_t *parent, const uint32_t *comp_size, uint32_t *comp_label,
+                    const int64_t *seeds, int64_t n_seeds, const uint32_t *n_seeds_dev,
+                    uint32_t *labels, cudaStream_t st) {
+    const uint64_t npix = (uint64_t)geom.zp * geom.yp * geom.xp;
+    uint32_t *n_comp = b.scalars + 0, *n_multi = b.scalars + 1, *counter = b.scalars + 2;
+    ISG_CUDA(cudaMemsetAsync(b.scalars, 0, 64 * sizeof(uint32_t), st));
+    if (n_seeds <= 0) return ISG_OK;
+    int blocks = (int)((n_seeds + 255) / 256);
+    seed_key_kernel<<<blocks, 256, 0, st>>>(seeds, n_seeds, n_seeds_dev, parent, npix, b.keys_a,
+                                            b.vals_a);
+    ISG_LAUNCHED();
+    size_t cub_bytes = b.cub_bytes;
+    ISG_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, cub_bytes, b.keys_a, b.keys_b, b.vals_a,
+                                             b.vals_b, (int)n_seeds, 0, 64, st));
+    count_launch(4);
+    comp_group_kernel<<<1, 1024, 0, st>>>(b.keys_b, b.vals_b, (uint32_t)n_seeds, comp_size,
+                                          comp_label, b.comp_start, b.arena_off, n_comp, n_multi);
+    ISG_LAUNCHED();
+    const int sms = num_sms();
+    fill_single_kernel<<<sms * 8, 256, 0, st>>>(parent, comp_label, mask, labels, npix);
+    ISG_LAUNCHED();
+    FloodWork w;
+    w.seed_keys = b.keys_b;
+    w.seed_labels = b.vals_b;
+    w.comp_start = b.comp_start;
+    w.arena_off = b.arena_off;
+    w.n_comp = n_comp;
+    w.arena_keys = b.arena_keys;
+    w.arena_idx = b.arena_idx;
+    w.counter = counter;
+    const size_t smem = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
+    int64_t grid = n_seeds / 2 + 1;                     // at most n_seeds/2 multi-seed components
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    flood_components_kernel<<<(int)grid, 32, smem, st>>>(geom, w, mask, labels);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+extern "C" size_t isg_flood_workspace_bytes(int64_t zp, int64_t yp, int64_t xp, int64_t max_seeds) {
+    const uint64_t npix = (uint64_t)zp * yp * xp;
+    Carver cv(nullptr, 0);
+    cv.take<uint8_t>(npix);        // domain
+    cv.take<uint32_t>(npix);       // parent
+    cv.take<uint32_t>(npix);       // comp_size
+    cv.take<uint32_t>(npix);       // comp_label
+    FloodStageBuffers b;
+    flood_stage_workspace(&b, cv, npix, max_seeds);
+    return cv.off + 512;
+}
+
+extern "C" int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, int aff_origin,
+                                  const float *aff_div, const uint8_t *mask, const int64_t *seeds,
+                                  int64_t n_seeds, uint32_t *labels, int64_t zp, int64_t yp,
+                                  int64_t xp, const float *aff_scale_host, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    ISG_REQUIRE(aff && aff_div && mask && labels, ISG_ERR_ARG, "isg_affinity_flood: null pointer");
+    ISG_REQUIRE(zp >= 3 && yp >= 3 && xp >= 3, ISG_ERR_ARG,
+                "isg_affinity_flood: padded extents must be >= 3 (got %lld,%lld,%lld)",
+                (long long)zp, (long long)yp, (long long)xp);
+    ISG_REQUIRE(aff_origin == 0 || aff_origin == 1, ISG_ERR_ARG, "aff_origin must be 0 or 1");
+    ISG_REQUIRE(n_seeds >= 0 && (n_seeds == 0 || seeds), ISG_ERR_ARG, "bad seeds");
+    const uint64_t npix = (uint64_t)zp * yp * xp;
+    ISG_REQUIRE(npix < 0xFFFFFFF0ull, ISG_ERR_OVERFLOW, "volume too large for 32-bit voxel ids");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(workspace, workspace_bytes);
+    uint8_t *dom = cv.take<uint8_t>(npix);
+    uint32_t *parent = cv.take<uint32_t>(npix);
+    uint32_t *comp_size = cv.take<uint32_t>(npix);
+    uint32_t *comp_label = cv.take<uint32_t>(npix);
+    FloodStageBuffers b;
+    flood_stage_workspace(&b, cv, npix, n_seeds);
+    ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE,
+                "isg_affinity_flood: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+    const int sms = num_sms();
+    const int grid = sms * 8;
+    domain_kernel<<<grid, 256, 0, st>>>(mask, labels, dom, npix);
+    ISG_LAUNCHED();
+    if (n_seeds > 0) {
+        seed_label_kernel<<<(int)((n_seeds + 255) / 256), 256, 0, st>>>(seeds, n_seeds, labels, dom,
+                                                                        npix);
+        ISG_LAUNCHED();
+    }
+    ISG_CUDA(cudaMemsetAsync(comp_size, 0, npix * sizeof(uint32_t), st));
+    ISG_CUDA(cudaMemsetAsync(comp_label, 0, npix * sizeof(uint32_t), st));
+    {
+        int rc = ccl_run(dom, parent, comp_size, (uint32_t)zp, (uint32_t)yp, (uint32_t)xp, st);
+        if (rc != ISG_OK) return rc;
+    }
+    FloodGeom g;
+    g.aff = aff;
+    g.plane_stride = aff_plane_stride;
+    g.origin = aff_origin;
+    g.za = (uint32_t)(zp - 2 * aff_origin);
+    g.ya = (uint32_t)(yp - 2 * aff_origin);
+    g.xa = (uint32_t)(xp - 2 * aff_origin);
+    g.div = aff_div;
+    for (int a = 0; a < 3; ++a) g.scale[a] = aff_scale_host ? fabsf(aff_scale_host[a]) : 1.0f;
+    g.zp = (uint32_t)zp;
+    g.yp = (uint32_t)yp;
+    g.xp = (uint32_t)xp;
+    return flood_stage_run(b, g, mask, parent, comp_size, comp_label, seeds, n_seeds, nullptr, labels,
+                           st);
+}

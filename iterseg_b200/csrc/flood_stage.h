@@ -1,0 +1,51 @@
+// Shared flood stage (CCL + component grouping + single-seed fill + ordered flood):
+// declarations only, the kernels live in flood.cu.
+#pragma once
+#include "common.cuh"
+
+namespace isg {
+
+static constexpr uint32_t CCL_NONE = 0xFFFFFFFFu;
+static constexpr uint32_t LABEL_MULTI = 0xFFFFFFFFu;
+
+struct FloodGeom {
+    const float *aff;          // 3 planes
+    int64_t plane_stride;
+    int origin;                // 0: planes padded like labels, 1: unpadded
+    uint32_t za, ya, xa;       // plane extents
+    const float *div;          // device float[3]
+    float scale[3];
+    uint32_t zp, yp, xp;
+};
+
+struct FloodStageBuffers {
+    uint64_t *keys_a, *keys_b;
+    uint32_t *vals_a, *vals_b;
+    uint32_t *comp_start;
+    uint64_t *arena_off;
+    uint32_t *scalars;          // [0]=n_comp [1]=n_multi [2]=work cursor
+    unsigned char *cub_tmp;
+    size_t cub_bytes;
+    uint64_t *arena_keys;
+    uint32_t *arena_idx;
+    uint64_t arena_cap;
+};
+
+// 6-connected components of the non-zero voxels of `dom` (padded volume):
+// parent[v] = smallest flat index of v's component (CCL_NONE outside),
+// comp_size[root] = voxel count (comp_size must be zero on entry).
+int ccl_run(const uint8_t *dom, uint32_t *parent, uint32_t *comp_size, uint32_t zp, uint32_t yp,
+            uint32_t xp, cudaStream_t st);
+
+size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds);
+
+// parent: flattened CCL roots of the flood domain (CCL_NONE outside);
+// comp_size: voxels per root; comp_label: zeroed scratch indexed by root;
+// seeds: padded flat indices in label order, labels[seed] already set; n_seeds is the
+// host-side (upper bound on the) count, n_seeds_dev the exact device-side count or NULL.
+int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uint8_t *mask,
+                    const uint32_t *parent, const uint32_t *comp_size, uint32_t *comp_label,
+                    const int64_t *seeds, int64_t n_seeds, const uint32_t *n_seeds_dev,
+                    uint32_t *labels, cudaStream_t st);
+
+}  // namespace isg

@@ -1,0 +1,507 @@
+// Feature map -> labels on the device: isg_segment_features.
+//
+// Replaces segment_output_image (src/iterseg/watershed.py:165-223):
+//   affinity normalisation   :194-201  (per-channel max; the divide is done inside the flood)
+//   _get_centroids           :232-236  (gaussian (0,1,1) -> 3x3x3 peaks > 0.04, sorted)
+//   _get_mask                :226-229  (otsu of the sigma=2 smoothed channel; raw > thr)
+//   _remove_unwanted_objects :239-251  (6-connected components, size window, seed filter)
+//   affinity_watershed       :17-35    (flood_stage_run)
+//
+// Arithmetic contracts (so that results are identical to scipy / numpy, see
+// SURVEY.md Appendix B and oracle/skimage_shim.py):
+//   * each 1-D Gaussian pass accumulates in float64 in scipy's order
+//     x[c]*w[0] + sum_{j=r..1} (x[c-j] + x[c+j])*w[j], no FMA contraction, boundary
+//     'nearest', and stores float32 between passes;
+//   * the histogram bin index, the float32 bin edges / centres and the float32
+//     sequential cumulative sums follow numpy.histogram / numpy.cumsum.
+#include <cub/cub.cuh>
+
+#include "flood_stage.h"
+
+namespace isg {
+
+struct GaussW {
+    double w[12];
+    int r;
+};
+
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+gauss_axis_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t Z, uint32_t Y,
+                  uint32_t X, GaussW gw, uint32_t *minmax /* nullable: ordered min, max */) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t len = AXIS == 0 ? Z : (AXIS == 1 ? Y : X);
+    const uint64_t step = AXIS == 0 ? (uint64_t)Y * X : (AXIS == 1 ? (uint64_t)X : 1ull);
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        uint32_t x = (uint32_t)(v % X);
+        uint64_t t = v / X;
+        uint32_t y = (uint32_t)(t % Y);
+        uint32_t z = (uint32_t)(t / Y);
+        const uint32_t c = AXIS == 0 ? z : (AXIS == 1 ? y : x);
+        const uint64_t line0 = v - (uint64_t)c * step;
+        double acc = __dmul_rn((double)in[v], gw.w[0]);
+        for (int j = gw.r; j >= 1; --j) {
+            uint32_t a = c >= (uint32_t)j ? c - j : 0u;
+            uint32_t b = c + j < len ? c + j : len - 1;
+            double s = __dadd_rn((double)__ldg(in + line0 + a * step), (double)__ldg(in + line0 + b * step));
+            acc = __dadd_rn(acc, __dmul_rn(s, gw.w[j]));
+        }
+        float o = (float)acc;
+        out[v] = o;
+        if (minmax) {
+            uint32_t k = f32_ord(o);
+            lo = min(lo, k);
+            hi = max(hi, k);
+        }
+    }
+    if (minmax) {
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(minmax + 0, lo);
+            atomicMax(minmax + 1, hi);
+        }
+    }
+}
+
+// per-channel maximum of up to 3 planes (np.max(affinities, axis=(1,2,3)), watershed.py:195)
+__global__ void __launch_bounds__(256)
+chan_max_kernel(const float *__restrict__ feats, uint64_t n, int c0, int c1, int c2,
+                uint32_t *__restrict__ out_ord) {
+    const int ch = blockIdx.y == 0 ? c0 : (blockIdx.y == 1 ? c1 : c2);
+    const float *base = feats + (uint64_t)ch * n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    float m = -INFINITY;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(base);
+        const uint64_t n4 = n / 4;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v = __ldg(p + i);
+            m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, base[n4 * 4 + threadIdx.x]);
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            m = fmaxf(m, __ldg(base + i));
+    }
+    uint32_t k = __reduce_max_sync(0xFFFFFFFFu, f32_ord(m));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_ord + blockIdx.y, k);
+}
+
+__global__ void ord_to_float_kernel(const uint32_t *__restrict__ in, float *__restrict__ out, int n) {
+    int i = threadIdx.x;
+    if (i < n) out[i] = ord_f32(in[i]);
+}
+
+// 3x3x3 peaks of the smoothed centre map (peak_local_max)
+__global__ void __launch_bounds__(256)
+local_max_kernel(const float *__restrict__ cs, uint32_t Z, uint32_t Y, uint32_t X, float thr,
+                 uint64_t *__restrict__ cand, uint32_t cap, uint32_t *__restrict__ n_cand,
+                 uint32_t *__restrict__ nontrivial) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool saw_nonmax = false;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        uint32_t x = (uint32_t)(v % X);
+        uint64_t t = v / X;
+        uint32_t y = (uint32_t)(t % Y);
+        uint32_t z = (uint32_t)(t / Y);
+        const float c = cs[v];
+        bool is_max = true;
+        const uint32_t z0 = z ? z - 1 : 0, z1 = z + 1 < Z ? z + 1 : Z - 1;
+        const uint32_t y0 = y ? y - 1 : 0, y1 = y + 1 < Y ? y + 1 : Y - 1;
+        const uint32_t x0 = x ? x - 1 : 0, x1 = x + 1 < X ? x + 1 : X - 1;
+        for (uint32_t zz = z0; zz <= z1; ++zz)
+            for (uint32_t yy = y0; yy <= y1; ++yy) {
+                const float *row = cs + ((uint64_t)zz * Y + yy) * X;
+                for (uint32_t xx = x0; xx <= x1; ++xx) is_max &= !(__ldg(row + xx) > c);
+            }
+        if (!is_max) saw_nonmax = true;
+        const bool interior = z > 0 && z + 1 < Z && y > 0 && y + 1 < Y && x > 0 && x + 1 < X;
+        if (is_max && interior && c > thr) {
+            uint32_t slot = atomicAdd(n_cand, 1u);
+            if (slot < cap) cand[slot] = ((uint64_t)(~f32_ord(c)) << 32) | (uint64_t)v;
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, saw_nonmax) && (threadIdx.x & 31) == 0) atomicOr(nontrivial, 1u);
+}
+
+// numpy.histogram(smoothed, 256) bin index (uniform-bin fast path, float32)
+__device__ __forceinline__ int np_hist_bin(float a, float first, float denom, const float *edges) {
+    float f = __fmul_rn(__fdiv_rn(__fsub_rn(a, first), denom), 256.0f);
+    int idx = (int)f;
+    if (idx == 256) idx = 255;
+    if (a < edges[idx]) idx -= 1;
+    else if (a >= edges[idx + 1] && idx != 255) idx += 1;
+    return idx;
+}
+
+__global__ void hist_edges_kernel(const uint32_t *__restrict__ minmax, float *__restrict__ edges) {
+    // np.linspace(first, last, 257, dtype=float32): arange * step + first, last forced
+    const float first = ord_f32(minmax[0]), last = ord_f32(minmax[1]);
+    const float step = __fdiv_rn(__fsub_rn(last, first), 256.0f);
+    int i = threadIdx.x;
+    if (i <= 256) {
+        float e;
+        if (step == 0.0f) e = __fadd_rn(__fmul_rn(__fdiv_rn((float)i, 256.0f), __fsub_rn(last, first)), first);
+        else e = __fadd_rn(__fmul_rn((float)i, step), first);
+        if (i == 256) e = last;
+        edges[i] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hist_kernel(const float *__restrict__ s, uint64_t n, const uint32_t *__restrict__ minmax,
+            const float *__restrict__ edges_g, unsigned long long *__restrict__ hist) {
+    __shared__ float edges[257];
+    __shared__ uint32_t h[256];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) edges[i] = edges_g[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const float first = ord_f32(minmax[0]), last = ord_f32(minmax[1]);
+    const float denom = __fsub_rn(last, first);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (denom > 0.0f) {
+        for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+            atomicAdd(&h[np_hist_bin(__ldg(s + v), first, denom, edges)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (h[i]) atomicAdd(hist + i, (unsigned long long)h[i]);
+}
+
+// skimage.filters.threshold_otsu on the 256-bin histogram, float32 sequential
+// arithmetic exactly as numpy evaluates it (oracle/skimage_shim.py).
+__global__ void otsu_kernel(const unsigned long long *__restrict__ hist,
+                            const float *__restrict__ edges, const uint32_t *__restrict__ minmax,
+                            float *__restrict__ thr_out) {
+    __shared__ float cnt[256], ctr[256], w1[256], w2[256], m1[256], m2[256];
+    if (threadIdx.x != 0) return;
+    const float first = ord_f32(minmax[0]), last = ord_f32(minmax[1]);
+    if (!(last > first)) {          // constant image: threshold_otsu returns that value
+        *thr_out = first;
+        return;
+    }
+    for (int i = 0; i < 256; ++i) {
+        cnt[i] = (float)hist[i];
+        ctr[i] = __fdiv_rn(__fadd_rn(edges[i], edges[i + 1]), 2.0f);
+    }
+    float acc = 0.0f, accm = 0.0f;
+    for (int i = 0; i < 256; ++i) {
+        acc = i == 0 ? cnt[0] : __fadd_rn(acc, cnt[i]);
+        float pm = __fmul_rn(cnt[i], ctr[i]);
+        accm = i == 0 ? pm : __fadd_rn(accm, pm);
+        w1[i] = acc;
+        m1[i] = __fdiv_rn(accm, acc);
+    }
+    for (int i = 255; i >= 0; --i) {
+        acc = i == 255 ? cnt[255] : __fadd_rn(acc, cnt[i]);
+        float pm = __fmul_rn(cnt[i], ctr[i]);
+        accm = i == 255 ? pm : __fadd_rn(accm, pm);
+        w2[i] = acc;
+        m2[i] = __fdiv_rn(accm, acc);
+    }
+    int best = 0;
+    float bestv = 0.0f;
+    for (int i = 0; i < 255; ++i) {
+        float d = __fsub_rn(m1[i], m2[i + 1]);
+        float var = __fmul_rn(__fmul_rn(w1[i], w2[i + 1]), __fmul_rn(d, d));
+        if (i == 0 || var > bestv) {          // np.argmax: first maximum; NaN never arises here
+            best = i;
+            bestv = var;
+        }
+    }
+    *thr_out = ctr[best];
+}
+
+// mask = raw > thr, zero-padded by one voxel (watershed.py:207-213)
+__global__ void __launch_bounds__(256)
+mask_kernel(const float *__restrict__ raw, uint32_t Z, uint32_t Y, uint32_t X,
+            const float *__restrict__ thr_dev, float thr_abs, int use_abs,
+            uint8_t *__restrict__ mask) {
+    const uint32_t Yp = Y + 2, Xp = X + 2;
+    const uint64_t np = (uint64_t)(Z + 2) * Yp * Xp;
+    const float thr = use_abs ? thr_abs : *thr_dev;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < np; v += stride) {
+        uint32_t x = (uint32_t)(v % Xp);
+        uint64_t t = v / Xp;
+        uint32_t y = (uint32_t)(t % Yp);
+        uint32_t z = (uint32_t)(t / Yp);
+        uint8_t m = 0;
+        if (x >= 1 && x <= X && y >= 1 && y <= Y && z >= 1 && z <= Z)
+            m = __ldg(raw + ((uint64_t)(z - 1) * Y + (y - 1)) * X + (x - 1)) > thr ? 1 : 0;
+        mask[v] = m;
+    }
+}
+
+// Single CTA: walk the sorted candidates, keep those whose component survives the
+// size window (watershed.py:241-249), compact in order, label them 1..N.
+__global__ void __launch_bounds__(1024)
+seed_filter_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n_cand,
+                   const uint32_t *__restrict__ nontrivial, const uint32_t *__restrict__ parent,
+                   const uint32_t *__restrict__ comp_size, uint64_t min_area, uint64_t max_area,
+                   uint32_t Z, uint32_t Y, uint32_t X, int64_t *__restrict__ seeds_out,
+                   uint32_t cap, uint32_t *__restrict__ labels, uint32_t *__restrict__ n_kept_out) {
+    typedef cub::BlockScan<uint32_t, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ uint32_t carry;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    if (*nontrivial == 0) n_cand = 0;          // constant image: peak_local_max returns nothing
+    const uint32_t Yp = Y + 2, Xp = X + 2;
+    for (uint32_t base = 0; base < n_cand; base += 1024) {
+        uint32_t i = base + t;
+        uint32_t keep = 0;
+        uint64_t p = 0;
+        if (i < n_cand) {
+            uint32_t u = (uint32_t)(cand_sorted[i] & 0xFFFFFFFFu);
+            uint32_t x = u % X;
+            uint32_t r = u / X;
+            uint32_t y = r % Y;
+            uint32_t z = r / Y;
+            p = ((uint64_t)(z + 1) * Yp + (y + 1)) * Xp + (x + 1);
+            uint32_t root = parent[p];
+            if (root != CCL_NONE) {
+                uint64_t sz = comp_size[root];
+                keep = (sz >= min_area && sz < max_area) ? 1u : 0u;
+            }
+        }
+        uint32_t pos, total;
+        Scan(tmp).ExclusiveSum(keep, pos, total);
+        if (keep) {
+            uint32_t k = carry + pos;
+            if (k < cap) {
+                seeds_out[k] = (int64_t)p;
+                labels[p] = k + 1;
+            }
+        }
+        __syncthreads();
+        if (t == 0) carry += total;
+        __syncthreads();
+    }
+    if (t == 0) *n_kept_out = carry < cap ? carry : cap;
+}
+
+__global__ void __launch_bounds__(256)
+mask_keep_kernel(const uint8_t *__restrict__ mask0, const uint32_t *__restrict__ parent,
+                 const uint32_t *__restrict__ comp_size, uint64_t min_area, uint64_t max_area,
+                 uint8_t *__restrict__ mask_out, uint64_t np, uint32_t *__restrict__ n_components) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t roots = 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < np; v += stride) {
+        uint8_t m = 0;
+        uint32_t r = parent[v];
+        if (r != CCL_NONE) {
+            uint64_t sz = comp_size[r];
+            m = (sz >= min_area && sz < max_area) ? 1 : 0;
+            if (r == (uint32_t)v && m) roots++;
+        }
+        mask_out[v] = m;
+    }
+    roots = __reduce_add_sync(0xFFFFFFFFu, roots);
+    if ((threadIdx.x & 31) == 0 && roots) atomicAdd(n_components, roots);
+}
+
+__global__ void counts_kernel(const uint32_t *n_kept, const uint32_t *n_cand, const uint32_t *n_components,
+                              const uint32_t *n_multi, int64_t *out) {
+    out[0] = *n_kept;
+    out[1] = *n_cand;
+    out[2] = *n_components;
+    out[3] = *n_multi;
+}
+
+struct PostBuffers {
+    float *tmp_a, *tmp_b;
+    uint64_t *cand_a, *cand_b;
+    unsigned char *cub_tmp;
+    size_t cub_bytes;
+    uint32_t *scal;        // 0,1: minmax ord; 2: n_cand; 3: nontrivial; 4: n_kept; 5: n_components; 8..10: aff max ord
+    float *fscal;          // 0..2: aff max; 3: otsu thr
+    float *edges;
+    unsigned long long *hist;
+    uint8_t *mask0;
+    uint32_t *parent, *comp_size, *comp_label;
+    FloodStageBuffers flood;
+};
+
+static void post_carve(PostBuffers *b, Carver &cv, uint64_t n, uint64_t np, int64_t max_seeds) {
+    b->tmp_a = cv.take<float>(n);
+    b->tmp_b = cv.take<float>(n);
+    b->cand_a = cv.take<uint64_t>(max_seeds);
+    b->cand_b = cv.take<uint64_t>(max_seeds);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                   (int)max_seeds);
+    b->cub_bytes = cub_bytes + 256;
+    b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
+    b->scal = cv.take<uint32_t>(64);
+    b->fscal = cv.take<float>(64);
+    b->edges = cv.take<float>(320);
+    b->hist = cv.take<unsigned long long>(256);
+    b->mask0 = cv.take<uint8_t>(np);
+    b->parent = cv.take<uint32_t>(np);
+    b->comp_size = cv.take<uint32_t>(np);
+    b->comp_label = cv.take<uint32_t>(np);
+    flood_stage_workspace(&b->flood, cv, np, max_seeds);
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+extern "C" size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds) {
+    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0) return 0;
+    Carver cv(nullptr, 0);
+    PostBuffers b;
+    post_carve(&b, cv, (uint64_t)z * y * x, (uint64_t)(z + 2) * (y + 2) * (x + 2), max_seeds);
+    return cv.off + 512;
+}
+
+extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
+                                    const isg_post_params *prm, const double *gauss1_host,
+                                    const double *gauss2_host, uint32_t *labels, uint8_t *mask_out,
+                                    int64_t *seeds_out, int64_t max_seeds, int64_t *counts_out,
+                                    float *otsu_out, void *workspace, size_t workspace_bytes,
+                                    void *stream) {
+    ISG_REQUIRE(feats && prm && labels && mask_out && seeds_out && counts_out && otsu_out,
+                ISG_ERR_ARG, "isg_segment_features: null pointer");
+    ISG_REQUIRE(z >= 1 && y >= 1 && x >= 1 && max_seeds >= 1, ISG_ERR_ARG, "bad extents");
+    ISG_REQUIRE(prm->r1 >= 0 && prm->r1 <= 11 && prm->r2 >= 0 && prm->r2 <= 11, ISG_ERR_ARG,
+                "gaussian radius must be <= 11");
+    for (int i = 0; i < 3; ++i)
+        ISG_REQUIRE(prm->aff_ch[i] >= 0 && prm->aff_ch[i] < n_chan, ISG_ERR_ARG, "bad affinity channel");
+    ISG_REQUIRE(prm->mask_ch >= 0 && prm->mask_ch < n_chan && prm->cent_ch >= 0 && prm->cent_ch < n_chan,
+                ISG_ERR_ARG, "bad channel index");
+    const uint64_t n = (uint64_t)z * y * x;
+    const uint64_t np = (uint64_t)(z + 2) * (y + 2) * (x + 2);
+    ISG_REQUIRE(np < 0xFFFFFFF0ull, ISG_ERR_OVERFLOW, "volume too large for 32-bit voxel ids");
+    // the flood reads the affinity planes through one base pointer + stride
+    const int c0 = prm->aff_ch[0];
+    ISG_REQUIRE(prm->aff_ch[1] - c0 == prm->aff_ch[2] - prm->aff_ch[1], ISG_ERR_ARG,
+                "affinity channels must be equally spaced");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(workspace, workspace_bytes);
+    PostBuffers b;
+    post_carve(&b, cv, n, np, max_seeds);
+    ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE,
+                "isg_segment_features: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+    const uint32_t Z = (uint32_t)z, Y = (uint32_t)y, X = (uint32_t)x;
+    const int sms = num_sms();
+    const int grid = sms * 8;
+    GaussW g1, g2;
+    g1.r = prm->r1;
+    g2.r = prm->r2;
+    for (int i = 0; i <= prm->r1; ++i) g1.w[i] = gauss1_host[i];
+    for (int i = 0; i <= prm->r2; ++i) g2.w[i] = gauss2_host[i];
+
+    ISG_CUDA(cudaMemsetAsync(b.scal, 0, 64 * sizeof(uint32_t), st));
+    ISG_CUDA(cudaMemsetAsync(b.hist, 0, 256 * sizeof(unsigned long long), st));
+    {   // scal[0] = min accumulates downwards
+        const uint32_t init = 0xFFFFFFFFu;
+        ISG_CUDA(cudaMemcpyAsync(b.scal, &init, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    // ---- affinity channel maxima -------------------------------------------------
+    chan_max_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(feats, n, prm->aff_ch[0], prm->aff_ch[1],
+                                                     prm->aff_ch[2], b.scal + 8);
+    ISG_LAUNCHED();
+    ord_to_float_kernel<<<1, 32, 0, st>>>(b.scal + 8, b.fscal, 3);
+    ISG_LAUNCHED();
+    // ---- seeds --------------------------------------------------------------------
+    const float *cent = feats + (uint64_t)prm->cent_ch * n;
+    const float *smoothed_c = cent;
+    if (prm->r1 > 0) {
+        gauss_axis_kernel<1><<<grid, 256, 0, st>>>(cent, b.tmp_a, Z, Y, X, g1, nullptr);
+        ISG_LAUNCHED();
+        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(b.tmp_a, b.tmp_b, Z, Y, X, g1, nullptr);
+        ISG_LAUNCHED();
+        smoothed_c = b.tmp_b;
+    }
+    local_max_kernel<<<grid, 256, 0, st>>>(smoothed_c, Z, Y, X, prm->peak_thresh, b.cand_a,
+                                           (uint32_t)max_seeds, b.scal + 2, b.scal + 3);
+    ISG_LAUNCHED();
+    uint32_t n_cand = 0;
+    ISG_CUDA(cudaMemcpyAsync(&n_cand, b.scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ISG_CUDA(cudaStreamSynchronize(st));
+    ISG_REQUIRE(n_cand <= (uint64_t)max_seeds, ISG_ERR_OVERFLOW,
+                "isg_segment_features: %u seed candidates exceed max_seeds=%lld", n_cand,
+                (long long)max_seeds);
+    const uint64_t *cand_sorted = b.cand_a;
+    if (n_cand > 1) {
+        size_t cb = b.cub_bytes;
+        ISG_CUDA(cub::DeviceRadixSort::SortKeys(b.cub_tmp, cb, b.cand_a, b.cand_b, (int)n_cand, 0, 64, st));
+        count_launch(4);
+        cand_sorted = b.cand_b;
+    }
+    // ---- mask ---------------------------------------------------------------------
+    const float *mraw = feats + (uint64_t)prm->mask_ch * n;
+    if (!prm->use_absolute_thresh) {
+        const float *s = mraw;
+        if (prm->r2 > 0) {
+            gauss_axis_kernel<0><<<grid, 256, 0, st>>>(mraw, b.tmp_a, Z, Y, X, g2, nullptr);
+            ISG_LAUNCHED();
+            gauss_axis_kernel<1><<<grid, 256, 0, st>>>(b.tmp_a, b.tmp_b, Z, Y, X, g2, nullptr);
+            ISG_LAUNCHED();
+            gauss_axis_kernel<2><<<grid, 256, 0, st>>>(b.tmp_b, b.tmp_a, Z, Y, X, g2, b.scal);
+            ISG_LAUNCHED();
+            s = b.tmp_a;
+        } else {
+            // sigma = 0: min/max of the raw channel via an identity pass
+            GaussW id;
+            id.r = 0;
+            id.w[0] = 1.0;
+            gauss_axis_kernel<2><<<grid, 256, 0, st>>>(mraw, b.tmp_a, Z, Y, X, id, b.scal);
+            ISG_LAUNCHED();
+            s = b.tmp_a;
+        }
+        hist_edges_kernel<<<1, 288, 0, st>>>(b.scal, b.edges);
+        ISG_LAUNCHED();
+        hist_kernel<<<sms * 4, 256, 0, st>>>(s, n, b.scal, b.edges, b.hist);
+        ISG_LAUNCHED();
+        otsu_kernel<<<1, 32, 0, st>>>(b.hist, b.edges, b.scal, b.fscal + 3);
+        ISG_LAUNCHED();
+    }
+    if (prm->use_absolute_thresh)
+        ISG_CUDA(cudaMemcpyAsync(b.fscal + 3, &prm->absolute_thresh, sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+    mask_kernel<<<grid, 256, 0, st>>>(mraw, Z, Y, X, b.fscal + 3, prm->absolute_thresh,
+                                      prm->use_absolute_thresh, b.mask0);
+    ISG_LAUNCHED();
+    // ---- components + size window ---------------------------------------------------
+    ISG_CUDA(cudaMemsetAsync(b.comp_size, 0, np * sizeof(uint32_t), st));
+    ISG_CUDA(cudaMemsetAsync(b.comp_label, 0, np * sizeof(uint32_t), st));
+    {
+        int rc = ccl_run(b.mask0, b.parent, b.comp_size, Z + 2, Y + 2, X + 2, st);
+        if (rc != ISG_OK) return rc;
+    }
+    mask_keep_kernel<<<grid, 256, 0, st>>>(b.mask0, b.parent, b.comp_size, (uint64_t)prm->min_area,
+                                           (uint64_t)prm->max_area, mask_out, np, b.scal + 5);
+    ISG_LAUNCHED();
+    seed_filter_kernel<<<1, 1024, 0, st>>>(cand_sorted, n_cand, b.scal + 3, b.parent, b.comp_size,
+                                           (uint64_t)prm->min_area, (uint64_t)prm->max_area, Z, Y, X,
+                                           seeds_out, (uint32_t)max_seeds, labels, b.scal + 4);
+    ISG_LAUNCHED();
+    // ---- flood ----------------------------------------------------------------------
+    FloodGeom g;
+    g.aff = feats + (uint64_t)c0 * n;
+    g.plane_stride = (int64_t)(prm->aff_ch[1] - c0) * (int64_t)n;
+    g.origin = 1;
+    g.za = Z;
+    g.ya = Y;
+    g.xa = X;
+    g.div = b.fscal;
+    for (int a = 0; a < 3; ++a) g.scale[a] = fabsf(prm->scale[a]);
+    g.zp = Z + 2;
+    g.yp = Y + 2;
+    g.xp = X + 2;
+    int rc = flood_stage_run(b.flood, g, mask_out, b.parent, b.comp_size, b.comp_label, seeds_out,
+                             (int64_t)n_cand, b.scal + 4, labels, st);
+    if (rc != ISG_OK) return rc;
+    counts_kernel<<<1, 1, 0, st>>>(b.scal + 4, b.scal + 2, b.scal + 5, b.flood.scalars + 1, counts_out);
+    ISG_LAUNCHED();
+    ISG_CUDA(cudaMemcpyAsync(otsu_out, b.fscal + 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return ISG_OK;
+}
