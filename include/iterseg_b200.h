@@ -143,9 +143,11 @@ void isg_unet_plan_destroy(isg_unet_plan *plan);
 /* frame (Z,Y,X) float32 -> feats (5,Z,Y,X) float32: every voxel written by exactly
  * one chunk's cropped interior (predict.py:89-95). */
 int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream);
-/* debugging / parity: copy an intermediate activation of chunk `chunk` to fp32 NCDHW */
-int isg_unet_debug_activation(isg_unet_plan *plan, const char *name, int chunk, float *out,
-                              int64_t out_elems, void *stream);
+/* debugging / parity: run the network on `frame` up to and including the convolution
+ * `name` ("c0.conv0" ... "c8_0.conv1") and return its raw (pre-BatchNorm, bias-free)
+ * output for chunk `chunk` as fp32 NCDHW (out_elems = Cout*D*H*W of that level). */
+int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame, const char *name, int chunk,
+                              float *out, int64_t out_elems, void *stream);
 /* algorithmic FLOPs of one forward over all chunks of the plan (2*MAC of 18 conv + 4 tconv) */
 double isg_unet_plan_flops(const isg_unet_plan *plan);
 

@@ -39,7 +39,7 @@ SIGNATURES = {
                                    _vp, _sz]),
     'isg_unet_plan_destroy': (None, [_vp]),
     'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),
-    'isg_unet_debug_activation': (_i32, [_vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
+    'isg_unet_debug_activation': (_i32, [_vp, _vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
     'isg_unet_plan_flops': (_c.c_double, [_vp]),
 }
 

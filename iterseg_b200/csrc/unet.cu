@@ -1,10 +1,525 @@
-// placeholder (replaced by the tcgen05 U-Net)
-#include "common.cuh"
-extern "C" size_t isg_unet_packed_weight_bytes(void) { return 0; }
-extern "C" int isg_unet_weights_pack(const void *const *, int, void *, void *) { isg::set_error("unet: not built yet"); return ISG_ERR_ARG; }
-extern "C" size_t isg_unet_workspace_bytes(int, int, int, int) { return 0; }
-extern "C" isg_unet_plan *isg_unet_plan_create(const void *, int, int, int, int, int64_t, int64_t, int64_t, const int32_t *, const int32_t *, const int32_t *, void *, size_t) { isg::set_error("unet: not built yet"); return nullptr; }
-extern "C" void isg_unet_plan_destroy(isg_unet_plan *) {}
-extern "C" int isg_unet_forward_chunks(isg_unet_plan *, const float *, float *, void *) { return ISG_ERR_ARG; }
-extern "C" int isg_unet_debug_activation(isg_unet_plan *, const char *, int, float *, int64_t, void *) { return ISG_ERR_ARG; }
-extern "C" double isg_unet_plan_flops(const isg_unet_plan *) { return 0.0; }
+// U-Net over chunks: plan (buffers, TMA tensor maps, tile geometry), weight packing
+// and the forward pass.  C-ABI: isg_unet_* (include/iterseg_b200.h).
+//
+// Replaces process_chunks + predict_chunk_feature_map (src/iterseg/predict.py:64-126)
+// and UNet.forward (src/iterseg/unet.py:284-364) for UNet(in_channels=1, out_channels=5).
+// BatchNorm runs with per-chunk batch statistics exactly like the reference, which
+// never calls .eval() (predict.py:25-35,118-123); conv biases are dropped because the
+// mean subtraction cancels them.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "unet_conv.cuh"
+#include "unet_elem.cuh"
+
+namespace isg {
+
+// ---- static architecture tables (unet.py:192-210, decoder_instructions :8-21) ----------
+struct ConvDef {
+    const char *name;
+    int cin, cout, level;
+};
+static const ConvDef CONVS[18] = {
+    {"c0.conv0", 1, 32, 0},     {"c0.conv1", 32, 32, 0},    {"c1.conv0", 32, 64, 1},
+    {"c1.conv1", 64, 64, 1},    {"c2.conv0", 64, 128, 2},   {"c2.conv1", 128, 128, 2},
+    {"c3.conv0", 128, 256, 3},  {"c3.conv1", 256, 256, 3},  {"c4.conv0", 256, 256, 4},
+    {"c4.conv1", 256, 256, 4},  {"c5_0.conv0", 512, 128, 3}, {"c5_0.conv1", 128, 128, 3},
+    {"c6_0.conv0", 256, 64, 2}, {"c6_0.conv1", 64, 64, 2},  {"c7_0.conv0", 128, 32, 1},
+    {"c7_0.conv1", 32, 32, 1},  {"c8_0.conv0", 64, 5, 0},   {"c8_0.conv1", 5, 5, 0}};
+static const int UP_C[4] = {256, 128, 64, 32};
+static const int UP_KZ[4] = {2, 1, 1, 1};
+
+static inline int cout_pad(int i) { return CONVS[i].cout == 5 ? 16 : CONVS[i].cout; }
+static inline bool is_tc(int i) { return i != 0 && i != 17; }
+
+struct PackLayout {
+    size_t w[18];          // conv weights (fp16 tap-major for tensor-core layers, fp32 otherwise)
+    size_t gamma[18], beta[18];
+    size_t up_w[4], up_b[4];
+    size_t total;
+};
+static PackLayout pack_layout() {
+    PackLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    for (int i = 0; i < 18; ++i) {
+        if (is_tc(i)) L.w[i] = take((size_t)27 * cout_pad(i) * CONVS[i].cin * sizeof(__half));
+        else L.w[i] = take((size_t)27 * CONVS[i].cin * CONVS[i].cout * sizeof(float));
+        L.gamma[i] = take(CONVS[i].cout * sizeof(float));
+        L.beta[i] = take(CONVS[i].cout * sizeof(float));
+    }
+    for (int u = 0; u < 4; ++u) {
+        L.up_w[u] = take((size_t)UP_C[u] * UP_KZ[u] * 4 * sizeof(float));
+        L.up_b[u] = take(UP_C[u] * sizeof(float));
+    }
+    L.total = off;
+    return L;
+}
+
+// ---- driver entry point for tensor maps (no link-time dependency on libcuda) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool make_act_map(CUtensorMap *m, const void *base, int C, int W, int H, int D, int N,
+                         int cblk, int P, int Ht) {
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                             (cuuint64_t)D * H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)cblk, (cuuint32_t)P, (cuuint32_t)(Ht + 2), 3u, 1u};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(base), dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d D=%d N=%d box %d,%d,%d) -> %d",
+                                     C, W, H, D, N, cblk, P, Ht + 2, (int)r);
+    return r == CUDA_SUCCESS;
+}
+static bool make_w_map(CUtensorMap *m, const void *base, int cin, int coutp, int cblk) {
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)coutp, 27};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)coutp * cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)cblk, (cuuint32_t)coutp, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled(weights cin=%d cout=%d) -> %d", cin, coutp, (int)r);
+    return r == CUDA_SUCCESS;
+}
+
+// ---- plan -------------------------------------------------------------------------------
+struct TcLayer {
+    ConvGeom g;
+    CUtensorMap tmA0, tmA1, tmB;
+    int cblk;
+    size_t smem;
+    int grid;
+};
+
+}  // namespace isg
+
+struct isg_unet_plan {
+    int N, Z, Y, X;
+    int D[5], H[5], W[5];
+    const unsigned char *packed;
+    isg::PackLayout L;
+    // device buffers
+    int *starts, *crop_lo, *crop_hi;
+    __half *raw[5], *act[5], *skip[4], *pooled[5], *up[4];
+    float *raw8, *raw9;
+    float *stats[18];
+    float *stats_all;
+    size_t stats_bytes;
+    isg::TcLayer tc[18];
+    int base_off_mode;
+    double flops;
+};
+
+namespace isg {
+
+static void choose_tile(int H, int W, int rb, int &P, int &Ht) {
+    long best = -1;
+    P = 32; Ht = 4;
+    for (int p = 10; p <= 130; ++p) {
+        const int ht = 130 / p;
+        if (ht < 1) continue;
+        const int wt = p - 2;
+        if (3L * (ht + 2) * p * rb > 80 * 1024) continue;
+        const long tiles = (long)((W + wt - 1) / wt) * ((H + ht - 1) / ht);
+        const long cost = tiles * 4096 + (long)(ht + 2) * p;      // fewest tiles, then smallest halo
+        if (best < 0 || cost < best) {
+            best = cost;
+            P = p;
+            Ht = ht;
+        }
+    }
+}
+
+static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
+    const int N = p->N;
+    auto vox = [&](int l) { return (size_t)N * p->D[l] * p->H[l] * p->W[l]; };
+    static const int CH[5] = {32, 64, 128, 256, 256};
+    p->starts = cv.take<int>(N * 3);
+    p->crop_lo = cv.take<int>(N * 3);
+    p->crop_hi = cv.take<int>(N * 3);
+    for (int l = 0; l < 5; ++l) {
+        p->raw[l] = cv.take<__half>(vox(l) * CH[l]);
+        p->act[l] = cv.take<__half>(vox(l) * CH[l]);
+        if (l < 4) {
+            p->skip[l] = cv.take<__half>(vox(l) * CH[l]);
+            p->up[l] = cv.take<__half>(vox(l) * CH[l]);
+        }
+        if (l > 0) p->pooled[l] = cv.take<__half>(vox(l) * CH[l - 1]);
+        else p->pooled[l] = nullptr;
+    }
+    p->raw8 = cv.take<float>(vox(0) * 8);
+    p->raw9 = cv.take<float>(vox(0) * 8);
+    size_t floats = 0;
+    for (int i = 0; i < 18; ++i) floats += (size_t)N * cout_pad(i) * 2;
+    p->stats_all = cv.take<float>(floats);
+    p->stats_bytes = floats * sizeof(float);
+    if (p->stats_all) {
+        float *s = p->stats_all;
+        for (int i = 0; i < 18; ++i) {
+            p->stats[i] = s;
+            s += (size_t)N * cout_pad(i) * 2;
+        }
+    }
+    return cv.off;
+}
+
+static bool level_dims(isg_unet_plan *p, int cz, int cy, int cx) {
+    p->D[0] = cz; p->H[0] = cy; p->W[0] = cx;
+    for (int l = 1; l < 5; ++l) {
+        p->D[l] = l == 4 ? p->D[l - 1] / 2 : p->D[l - 1];
+        p->H[l] = p->H[l - 1] / 2 + 1;
+        p->W[l] = p->W[l - 1] / 2 + 1;
+    }
+    // the decoder's crops must reproduce the skip shapes (unet.py:329-345), else torch.cat fails
+    bool ok = cz >= 2 && cz % 2 == 0;
+    for (int l = 3; l >= 1; --l) ok = ok && 2 * p->H[l + 1] - 1 == p->H[l] && 2 * p->W[l + 1] - 1 == p->W[l];
+    ok = ok && 2 * p->H[1] - 2 == p->H[0] && 2 * p->W[1] - 2 == p->W[0];
+    return ok;
+}
+
+static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, const __half *src1,
+                           int c1, void *out, int out_mode) {
+    TcLayer &t = p->tc[i];
+    const int l = CONVS[i].level;
+    const int cin = CONVS[i].cin;
+    const int cblk = (c0 % 64 == 0 && (c1 % 64 == 0)) ? 64 : 32;
+    t.cblk = cblk;
+    ConvGeom &g = t.g;
+    g.N = p->N; g.D = p->D[l]; g.H = p->H[l]; g.W = p->W[l];
+    choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+    g.Wt = g.P - 2;
+    g.tiles_w = (g.W + g.Wt - 1) / g.Wt;
+    g.tiles_h = (g.H + g.Ht - 1) / g.Ht;
+    g.n_tiles = g.N * g.D * g.tiles_h * g.tiles_w;
+    g.cout = cout_pad(i);
+    g.nkb0 = c0 / cblk;
+    g.nkb1 = c1 / cblk;
+    g.a_rows = 3 * (g.Ht + 2) * g.P;
+    g.a_stage_bytes = (g.a_rows * cblk * 2 + 1023) & ~1023;
+    g.b_stage_bytes = g.cout * cblk * 2;
+    const long fixed = 1024 + 2L * g.a_stage_bytes + CONV_SLACK + 512 + 4 * 32 * 33 * 4;
+    long nb = (232448 - fixed) / g.b_stage_bytes;
+    if (nb > 12) nb = 12;
+    if (nb < 2) {
+        set_error("conv %s: shared memory budget exceeded", CONVS[i].name);
+        return false;
+    }
+    g.n_b_stages = (int)nb;
+    g.out_mode = out_mode;
+    g.base_off_mode = p->base_off_mode;
+    g.out = out;
+    g.stats = p->stats[i];
+    t.smem = conv_smem_bytes(g);
+    t.grid = g.n_tiles < num_sms() ? g.n_tiles : num_sms();
+    if (!make_act_map(&t.tmA0, src0, c0, g.W, g.H, g.D, g.N, cblk, g.P, g.Ht)) return false;
+    if (c1 > 0) {
+        if (!make_act_map(&t.tmA1, src1, c1, g.W, g.H, g.D, g.N, cblk, g.P, g.Ht)) return false;
+    } else {
+        t.tmA1 = t.tmA0;
+    }
+    if (!make_w_map(&t.tmB, p->packed + p->L.w[i], cin, g.cout, cblk)) return false;
+    return true;
+}
+
+static int launch_tc(const TcLayer &t, cudaStream_t st) {
+    if (t.cblk == 64) {
+        ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+        conv3d_tc_kernel<64><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
+    } else {
+        ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+        conv3d_tc_kernel<32><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
+    }
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+static inline dim3 egrid(size_t work, int N) {
+    size_t b = (work + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return dim3((unsigned)b, (unsigned)N);
+}
+
+// run the network up to and including conv `stop` (17 = everything incl. placement)
+static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop, cudaStream_t st) {
+    const int N = p->N;
+    const unsigned char *pk = p->packed;
+    const PackLayout &L = p->L;
+    auto G = [&](int i) { return reinterpret_cast<const float *>(pk + L.gamma[i]); };
+    auto B = [&](int i) { return reinterpret_cast<const float *>(pk + L.beta[i]); };
+    auto vox = [&](int l) { return (size_t)p->D[l] * p->H[l] * p->W[l]; };
+    ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
+    // ---- c0.conv0 (CUDA cores, straight from the frame) ----
+    conv_in_kernel<<<egrid(vox(0), N), 256, 0, st>>>(frame, p->Z, p->Y, p->X, p->starts,
+                                                     reinterpret_cast<const float *>(pk + L.w[0]),
+                                                     p->raw[0], p->stats[0], p->D[0], p->H[0], p->W[0]);
+    ISG_LAUNCHED();
+    if (stop == 0) return ISG_OK;
+    static const int CH[5] = {32, 64, 128, 256, 256};
+    // ---- encoder ----
+    for (int l = 0; l < 5; ++l) {
+        const int i0 = 2 * l, i1 = 2 * l + 1;
+        if (l > 0) {
+            int rc = launch_tc(p->tc[i0], st);
+            if (rc) return rc;
+            if (stop == i0) return ISG_OK;
+        }
+        bn_relu_kernel<<<egrid(vox(l) * CH[l] / 8, N), 256, 0, st>>>(p->raw[l], p->act[l], p->stats[i0],
+                                                                     G(i0), B(i0), CH[l], vox(l));
+        ISG_LAUNCHED();
+        int rc = launch_tc(p->tc[i1], st);
+        if (rc) return rc;
+        if (stop == i1) return ISG_OK;
+        if (l < 4) {
+            const size_t work = vox(l + 1) * CH[l] / 8;
+            if (l == 3)
+                bn_relu_pool_kernel<2><<<egrid(work, N), 256, 0, st>>>(
+                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), CH[l], p->D[l],
+                    p->H[l], p->W[l], p->D[l + 1], p->H[l + 1], p->W[l + 1]);
+            else
+                bn_relu_pool_kernel<1><<<egrid(work, N), 256, 0, st>>>(
+                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), CH[l], p->D[l],
+                    p->H[l], p->W[l], p->D[l + 1], p->H[l + 1], p->W[l + 1]);
+            ISG_LAUNCHED();
+        }
+    }
+    // ---- decoder: level 4 -> 3 -> 2 -> 1 -> 0 ----
+    for (int u = 0; u < 4; ++u) {
+        const int lc = 4 - u, lf = 3 - u;           // coarse (source) and fine (target) level
+        const int src_conv = u == 0 ? 9 : 9 + 2 * u; // conv whose raw output feeds this upsample
+        const int C = UP_C[u];
+        const float *uw = reinterpret_cast<const float *>(pk + L.up_w[u]);
+        const float *ub = reinterpret_cast<const float *>(pk + L.up_b[u]);
+        const size_t work = vox(lc) * C / 8;
+        const int off = u == 3 ? 1 : 0;
+        if (u == 0)
+            bn_relu_up_kernel<2><<<egrid(work, N), 256, 0, st>>>(
+                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
+                p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
+        else
+            bn_relu_up_kernel<1><<<egrid(work, N), 256, 0, st>>>(
+                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
+                p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
+        ISG_LAUNCHED();
+        const int i0 = 10 + 2 * u, i1 = i0 + 1;
+        int rc = launch_tc(p->tc[i0], st);          // reads [up, skip] of level lf
+        if (rc) return rc;
+        if (stop == i0) return ISG_OK;
+        if (u < 3) {
+            const int Cm = CONVS[i0].cout;
+            bn_relu_kernel<<<egrid(vox(lf) * Cm / 8, N), 256, 0, st>>>(p->raw[lf], p->act[lf], p->stats[i0],
+                                                                       G(i0), B(i0), Cm, vox(lf));
+            ISG_LAUNCHED();
+            rc = launch_tc(p->tc[i1], st);
+            if (rc) return rc;
+            if (stop == i1) return ISG_OK;
+        }
+    }
+    // ---- c8_0.conv1 (5 -> 5) + BN + sigmoid + placement ----
+    conv_out_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw8, p->stats[16], G(16), B(16),
+                                                      reinterpret_cast<const float *>(pk + L.w[17]),
+                                                      p->raw9, p->stats[17], p->D[0], p->H[0], p->W[0]);
+    ISG_LAUNCHED();
+    if (feats == nullptr) return ISG_OK;
+    place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), p->starts,
+                                                   p->crop_lo, p->crop_hi, feats, p->Z, p->Y, p->X,
+                                                   p->D[0], p->H[0], p->W[0]);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+extern "C" size_t isg_unet_packed_weight_bytes(void) { return pack_layout().total; }
+
+extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, void *packed, void *stream) {
+    ISG_REQUIRE(tensors && packed, ISG_ERR_ARG, "isg_unet_weights_pack: null pointer");
+    ISG_REQUIRE(n_tensors == 134, ISG_ERR_ARG,
+                "isg_unet_weights_pack: expected the 134 tensors of UNet(1,5).state_dict(), got %d", n_tensors);
+    cudaStream_t st = (cudaStream_t)stream;
+    const PackLayout L = pack_layout();
+    unsigned char *pk = (unsigned char *)packed;
+    ISG_CUDA(cudaMemsetAsync(packed, 0, L.total, st));
+    for (int i = 0; i < 18; ++i) {
+        const int mi = i / 2, ci = i % 2;
+        const float *w = (const float *)tensors[14 * mi + 2 * ci];
+        const float *gam = (const float *)tensors[14 * mi + 4 + 5 * ci];
+        const float *bet = (const float *)tensors[14 * mi + 5 + 5 * ci];
+        ISG_REQUIRE(w && gam && bet, ISG_ERR_ARG, "isg_unet_weights_pack: missing tensor for %s", CONVS[i].name);
+        if (is_tc(i))
+            pack_conv_w_kernel<<<256, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, cout_pad(i), CONVS[i].cin);
+        else
+            pack_conv_w_f32_kernel<<<16, 256, 0, st>>>(w, (float *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
+        ISG_LAUNCHED();
+        copy_f32_kernel<<<1, 256, 0, st>>>(gam, (float *)(pk + L.gamma[i]), CONVS[i].cout);
+        ISG_LAUNCHED();
+        copy_f32_kernel<<<1, 256, 0, st>>>(bet, (float *)(pk + L.beta[i]), CONVS[i].cout);
+        ISG_LAUNCHED();
+    }
+    for (int u = 0; u < 4; ++u) {
+        const float *w = (const float *)tensors[126 + 2 * u];
+        const float *b = (const float *)tensors[126 + 2 * u + 1];
+        ISG_REQUIRE(w && b, ISG_ERR_ARG, "isg_unet_weights_pack: missing up%d tensors", u);
+        copy_f32_kernel<<<4, 256, 0, st>>>(w, (float *)(pk + L.up_w[u]), UP_C[u] * UP_KZ[u] * 4);
+        ISG_LAUNCHED();
+        copy_f32_kernel<<<1, 256, 0, st>>>(b, (float *)(pk + L.up_b[u]), UP_C[u]);
+        ISG_LAUNCHED();
+    }
+    return ISG_OK;
+}
+
+extern "C" size_t isg_unet_workspace_bytes(int n_chunks, int cz, int cy, int cx) {
+    if (n_chunks <= 0) return 0;
+    isg_unet_plan p;
+    memset(&p, 0, sizeof(p));
+    p.N = n_chunks;
+    if (!level_dims(&p, cz, cy, cx)) return 0;
+    Carver cv(nullptr, 0);
+    plan_carve(&p, cv);
+    return cv.off + 1024;
+}
+
+extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n_chunks, int cz, int cy,
+                                               int cx, int64_t z, int64_t y, int64_t x,
+                                               const int32_t *starts_host, const int32_t *crop_lo_host,
+                                               const int32_t *crop_hi_host, void *workspace,
+                                               size_t workspace_bytes) {
+    if (!packed_weights || !starts_host || !crop_lo_host || !crop_hi_host || !workspace || n_chunks <= 0) {
+        set_error("isg_unet_plan_create: bad argument");
+        return nullptr;
+    }
+    if (!encode_fn()) {
+        set_error("isg_unet_plan_create: cuTensorMapEncodeTiled is not available from the driver");
+        return nullptr;
+    }
+    isg_unet_plan *p = new isg_unet_plan();
+    memset((void *)p, 0, sizeof(*p));
+    p->N = n_chunks;
+    p->Z = (int)z; p->Y = (int)y; p->X = (int)x;
+    p->packed = (const unsigned char *)packed_weights;
+    p->L = pack_layout();
+    const char *bm = getenv("ISG_CONV_BASE_OFFSET");
+    p->base_off_mode = bm ? atoi(bm) : 1;
+    if (!level_dims(p, cz, cy, cx)) {
+        set_error("chunk shape (%d,%d,%d) is not valid for this U-Net: z must be even and y/x must survive "
+                  "four poolings and the decoder crops (e.g. 10,256,256)", cz, cy, cx);
+        delete p;
+        return nullptr;
+    }
+    for (int n = 0; n < n_chunks; ++n) {
+        const int32_t *s = starts_host + 3 * n;
+        if (s[0] < 0 || s[1] < 0 || s[2] < 0 || s[0] + cz > z || s[1] + cy > y || s[2] + cx > x) {
+            set_error("chunk %d starts outside the frame", n);
+            delete p;
+            return nullptr;
+        }
+    }
+    Carver cv(workspace, workspace_bytes);
+    plan_carve(p, cv);
+    if (!cv.ok) {
+        set_error("isg_unet_plan_create: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+        delete p;
+        return nullptr;
+    }
+    cudaMemcpy(p->starts, starts_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->crop_lo, crop_lo_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->crop_hi, crop_hi_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
+    bool ok = true;
+    // encoder
+    ok = ok && setup_tc_layer(p, 1, p->act[0], 32, nullptr, 0, p->raw[0], 0);
+    ok = ok && setup_tc_layer(p, 2, p->pooled[1], 32, nullptr, 0, p->raw[1], 0);
+    ok = ok && setup_tc_layer(p, 3, p->act[1], 64, nullptr, 0, p->raw[1], 0);
+    ok = ok && setup_tc_layer(p, 4, p->pooled[2], 64, nullptr, 0, p->raw[2], 0);
+    ok = ok && setup_tc_layer(p, 5, p->act[2], 128, nullptr, 0, p->raw[2], 0);
+    ok = ok && setup_tc_layer(p, 6, p->pooled[3], 128, nullptr, 0, p->raw[3], 0);
+    ok = ok && setup_tc_layer(p, 7, p->act[3], 256, nullptr, 0, p->raw[3], 0);
+    ok = ok && setup_tc_layer(p, 8, p->pooled[4], 256, nullptr, 0, p->raw[4], 0);
+    ok = ok && setup_tc_layer(p, 9, p->act[4], 256, nullptr, 0, p->raw[4], 0);
+    // decoder: concat order is [upsampled, skip] (unet.py:332,337,341,345)
+    ok = ok && setup_tc_layer(p, 10, p->up[3], 256, p->skip[3], 256, p->raw[3], 0);
+    ok = ok && setup_tc_layer(p, 11, p->act[3], 128, nullptr, 0, p->raw[3], 0);
+    ok = ok && setup_tc_layer(p, 12, p->up[2], 128, p->skip[2], 128, p->raw[2], 0);
+    ok = ok && setup_tc_layer(p, 13, p->act[2], 64, nullptr, 0, p->raw[2], 0);
+    ok = ok && setup_tc_layer(p, 14, p->up[1], 64, p->skip[1], 64, p->raw[1], 0);
+    ok = ok && setup_tc_layer(p, 15, p->act[1], 32, nullptr, 0, p->raw[1], 0);
+    ok = ok && setup_tc_layer(p, 16, p->up[0], 32, p->skip[0], 32, p->raw8, 1);
+    if (!ok) {
+        delete p;
+        return nullptr;
+    }
+    double macs = 0;
+    for (int i = 0; i < 18; ++i) {
+        const int l = CONVS[i].level;
+        macs += 27.0 * CONVS[i].cin * CONVS[i].cout * p->D[l] * p->H[l] * p->W[l];
+    }
+    for (int u = 0; u < 4; ++u) {
+        const int lc = 4 - u;
+        macs += (double)UP_C[u] * UP_KZ[u] * 4 * p->D[lc] * p->H[lc] * p->W[lc];
+    }
+    p->flops = 2.0 * macs * n_chunks;
+    return p;
+}
+
+extern "C" void isg_unet_plan_destroy(isg_unet_plan *plan) { delete plan; }
+
+extern "C" double isg_unet_plan_flops(const isg_unet_plan *plan) { return plan ? plan->flops : 0.0; }
+
+extern "C" int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream) {
+    ISG_REQUIRE(plan && frame && feats, ISG_ERR_ARG, "isg_unet_forward_chunks: null pointer");
+    return forward(plan, frame, feats, 17, (cudaStream_t)stream);
+}
+
+extern "C" int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame, const char *name,
+                                         int chunk, float *out, int64_t out_elems, void *stream) {
+    ISG_REQUIRE(plan && frame && name && out, ISG_ERR_ARG, "isg_unet_debug_activation: null pointer");
+    ISG_REQUIRE(chunk >= 0 && chunk < plan->N, ISG_ERR_ARG, "bad chunk index");
+    int idx = -1;
+    for (int i = 0; i < 18; ++i)
+        if (strcmp(name, CONVS[i].name) == 0) idx = i;
+    ISG_REQUIRE(idx >= 0, ISG_ERR_ARG, "unknown layer '%s' (use e.g. c0.conv0 ... c8_0.conv1)", name);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = forward(plan, frame, nullptr, idx, st);
+    if (rc) return rc;
+    const int l = CONVS[idx].level;
+    const size_t vox = (size_t)plan->D[l] * plan->H[l] * plan->W[l];
+    const int C = CONVS[idx].cout;
+    ISG_REQUIRE((int64_t)(vox * C) == out_elems, ISG_ERR_ARG, "out must hold %zu floats", vox * C);
+    const void *src;
+    int is_f32 = 0, cstride = cout_pad(idx);
+    if (idx == 16) { src = plan->raw8 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
+    else if (idx == 17) { src = plan->raw9 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
+    else src = plan->raw[l] + (size_t)chunk * vox * cstride;
+    debug_to_ncdhw_kernel<<<num_sms() * 4, 256, 0, st>>>(src, is_f32, cstride, C, vox, out);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}

@@ -1,0 +1,398 @@
+// Memory-bound companions of the tensor-core convolutions (all channels-last fp16,
+// fp32 math): train-mode BatchNorm apply + ReLU, fused with max-pool (encoder) or
+// with the depthwise transposed convolution + crop (decoder); the two CUDA-core
+// convolutions that are too thin for tensor cores (Cin = 1 and 5 -> 5); the final
+// BatchNorm + sigmoid + crop-and-place.
+//
+// Reference: ConvModule.forward (src/iterseg/unet.py:91-106), MaxPool3d layers
+// (unet.py:166-187), ConvTranspose3d layers (unet.py:216-242), crops + concat
+// (unet.py:329-345), process_chunks placement (predict.py:89-95).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace isg {
+
+static constexpr float BN_EPS = 1e-5f;
+
+// BatchNorm3d in training mode: batch statistics (biased variance) of ONE chunk.
+__device__ __forceinline__ void bn_coeffs(const float *stats_c, float gamma, float beta,
+                                          float inv_count, float &scale, float &shift) {
+    const float mean = stats_c[0] * inv_count;
+    const float var = fmaxf(stats_c[1] * inv_count - mean * mean, 0.0f);
+    const float inv = 1.0f / sqrtf(var + BN_EPS);
+    scale = gamma * inv;
+    shift = beta - mean * scale;
+}
+
+__device__ __forceinline__ void load8h(const __half *p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8h(__half *p, const float (&v)[8]) {
+    uint4 u;
+    __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+
+// shared scale/shift table for the chunk this block works on (C <= 256)
+__device__ __forceinline__ void bn_table(float *s_scale, float *s_shift, const float *stats,
+                                         const float *gamma, const float *beta, int C, int n,
+                                         float inv_count) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], inv_count, s_scale[c], s_shift[c]);
+    __syncthreads();
+}
+
+// raw -> relu(bn(raw)), same shape.  grid = (blocks, N)
+__global__ void __launch_bounds__(256)
+bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const float *__restrict__ stats,
+               const float *__restrict__ gamma, const float *__restrict__ beta, int C, size_t vox) {
+    __shared__ float s_scale[256], s_shift[256];
+    const int n = blockIdx.y;
+    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    const int groups = C / 8;
+    const size_t total = vox * groups;
+    const __half *src = raw + (size_t)n * vox * C;
+    __half *dst = act + (size_t)n * vox * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % groups) * 8;
+        float v[8];
+        load8h(src + i * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
+        store8h(dst + i * 8, v);
+    }
+}
+
+// Encoder: skip = relu(bn(raw)) at the fine level and pooled = maxpool(skip) with
+// kernel = stride = (PZ,2,2), padding (0,1,1) (-inf padding: border windows just see
+// fewer voxels).  One thread per (coarse voxel, 8 channels).  grid = (blocks, N)
+template <int PZ>
+__global__ void __launch_bounds__(256)
+bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
+                    __half *__restrict__ pooled, const float *__restrict__ stats,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, int C, int D,
+                    int H, int W, int Dc, int Hc, int Wc) {
+    __shared__ float s_scale[256], s_shift[256];
+    const int n = blockIdx.y;
+    const size_t vox = (size_t)D * H * W;
+    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    const int groups = C / 8;
+    const size_t total = (size_t)Dc * Hc * Wc * groups;
+    const __half *src = raw + (size_t)n * vox * C;
+    __half *dsk = skip + (size_t)n * vox * C;
+    __half *dpo = pooled + (size_t)n * Dc * Hc * Wc * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % groups) * 8;
+        size_t t = i / groups;
+        const int wc = (int)(t % Wc); t /= Wc;
+        const int hc = (int)(t % Hc);
+        const int dc = (int)(t / Hc);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 0.0f;           // post-ReLU values are >= 0
+        for (int kz = 0; kz < PZ; ++kz) {
+            const int d = dc * PZ + kz;
+            if (d >= D) continue;
+            for (int a = 0; a < 2; ++a) {
+                const int h = 2 * hc - 1 + a;
+                if (h < 0 || h >= H) continue;
+                for (int b = 0; b < 2; ++b) {
+                    const int w = 2 * wc - 1 + b;
+                    if (w < 0 || w >= W) continue;
+                    const size_t off = ((((size_t)d * H + h) * W + w) * C) + c0;
+                    float v[8];
+                    load8h(src + off, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[j] = fmaxf(fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
+                        // the pooled tensor holds the max of the fp16-ROUNDED skip values so that
+                        // it equals maxpool(skip) exactly
+                        v[j] = __half2float(__float2half_rn(v[j]));
+                        m[j] = fmaxf(m[j], v[j]);
+                    }
+                    store8h(dsk + off, v);
+                }
+            }
+        }
+        store8h(dpo + ((((size_t)dc * Hc + hc) * Wc + wc) * C) + c0, m);
+    }
+}
+
+// Decoder: up = crop(conv_transpose3d(relu(bn(raw)), w, b, kernel = stride = (KZ,2,2),
+// groups = C)).  out[c, KZ*d+kz, 2h+a-off, 2w+b-off] = wgt[c,kz,a,b] * x[c,d,h,w] + bias[c];
+// off = 0 with crop [:-1,:-1] (up0..up2), off = 1 with crop [1:-1,1:-1] (up3).
+// One thread per (coarse voxel, 8 channels).  grid = (blocks, N)
+template <int KZ>
+__global__ void __launch_bounds__(256)
+bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
+                  const float *__restrict__ stats, const float *__restrict__ gamma,
+                  const float *__restrict__ beta, const float *__restrict__ wgt,
+                  const float *__restrict__ bias, int C, int Dc, int Hc, int Wc, int Df, int Hf,
+                  int Wf, int off) {
+    __shared__ float s_scale[256], s_shift[256];
+    const int n = blockIdx.y;
+    const size_t vox = (size_t)Dc * Hc * Wc;
+    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    const int groups = C / 8;
+    const size_t total = vox * groups;
+    const __half *src = raw + (size_t)n * vox * C;
+    __half *dst = up + (size_t)n * Df * Hf * Wf * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % groups) * 8;
+        size_t t = i / groups;
+        const int wc = (int)(t % Wc); t /= Wc;
+        const int hc = (int)(t % Hc);
+        const int dc = (int)(t / Hc);
+        float x[8];
+        load8h(src + i * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = fmaxf(fmaf(x[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
+        for (int kz = 0; kz < KZ; ++kz) {
+            const int d = dc * KZ + kz;
+            if (d >= Df) continue;
+            for (int a = 0; a < 2; ++a) {
+                const int h = 2 * hc + a - off;
+                if (h < 0 || h >= Hf) continue;
+                for (int b = 0; b < 2; ++b) {
+                    const int w = 2 * wc + b - off;
+                    if (w < 0 || w >= Wf) continue;
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = fmaf(__ldg(wgt + (size_t)(c0 + j) * (KZ * 4) + kz * 4 + a * 2 + b), x[j],
+                                    __ldg(bias + c0 + j));
+                    store8h(dst + ((((size_t)d * Hf + h) * Wf + w) * C) + c0, o);
+                }
+            }
+        }
+    }
+}
+
+// block-wide reduction of NV per-thread partial sums -> atomicAdd into dst[i*stride]
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float *dst, int stride) {
+    __shared__ float red[8][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0) red[warp][i] = x;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        float x = 0.0f;
+        for (int w = 0; w < nw; ++w) x += red[w][i];
+        atomicAdd(dst + (size_t)i * stride, x);
+    }
+    __syncthreads();
+}
+
+// c0.conv0: Cin = 1 -> 32, fp32 CUDA cores, reads the chunk straight out of the frame
+// (zero padding at the CHUNK border, as the reference pads the sliced chunk).
+// starts: [N][3] chunk origins.  grid = (blocks, N), block 256.
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *__restrict__ starts,
+               const float *__restrict__ wgt /* [27][32] */, __half *__restrict__ raw,
+               float *__restrict__ stats, int D, int H, int W) {
+    __shared__ float w_s[27 * 32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) w_s[i] = wgt[i];
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int z0 = starts[n * 3 + 0], y0 = starts[n * 3 + 1], x0 = starts[n * 3 + 2];
+    const size_t vox = (size_t)D * H * W;
+    float ssum[32], ssq[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.0f;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vox;
+         v += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(v % W);
+        const size_t t = v / W;
+        const int h = (int)(t % H);
+        const int d = (int)(t / H);
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dd = d + tap / 9 - 1, hh = h + (tap / 3) % 3 - 1, ww = w + tap % 3 - 1;
+            float x = 0.0f;
+            if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                x = __ldg(frame + ((size_t)(z0 + dd) * Y + (y0 + hh)) * X + (x0 + ww));
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, w_s[tap * 32 + c], acc[c]);
+        }
+        __half *o = raw + ((size_t)n * vox + v) * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = acc[q * 8 + j];
+            store8h(o + q * 8, f);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            ssum[c] += acc[c];
+            ssq[c] = fmaf(acc[c], acc[c], ssq[c]);
+        }
+    }
+    block_reduce_atomic<32>(ssum, stats + (size_t)n * 32 * 2 + 0, 2);
+    block_reduce_atomic<32>(ssq, stats + (size_t)n * 32 * 2 + 1, 2);
+}
+
+// c8_0.conv1: 5 -> 5 on CUDA cores.  Input = relu(bn(raw8)) computed on the fly from the
+// fp32 [vox][8] output of c8_0.conv0 (stats8 has 16 columns per chunk), zero outside the
+// chunk.  Output raw9 fp32 [vox][8] + statistics [N][5][2].   grid = (blocks, N)
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const float *__restrict__ raw8, const float *__restrict__ stats8,
+                const float *__restrict__ gamma8, const float *__restrict__ beta8,
+                const float *__restrict__ wgt /* [27][5 in][5 out] */, float *__restrict__ raw9,
+                float *__restrict__ stats9, int D, int H, int W) {
+    __shared__ float w_s[27 * 25];
+    __shared__ float sc[5], sh[5];
+    const int n = blockIdx.y;
+    const size_t vox = (size_t)D * H * W;
+    for (int i = threadIdx.x; i < 27 * 25; i += blockDim.x) w_s[i] = wgt[i];
+    if (threadIdx.x < 5)
+        bn_coeffs(stats8 + ((size_t)n * 16 + threadIdx.x) * 2, gamma8[threadIdx.x], beta8[threadIdx.x],
+                  1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
+    __syncthreads();
+    float ssum[5], ssq[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ssum[c] = ssq[c] = 0.0f;
+    const float *src = raw8 + (size_t)n * vox * 8;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vox;
+         v += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(v % W);
+        const size_t t = v / W;
+        const int h = (int)(t % H);
+        const int d = (int)(t / H);
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dd = d + tap / 9 - 1, hh = h + (tap / 3) % 3 - 1, ww = w + tap % 3 - 1;
+            if (dd < 0 || dd >= D || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const float4 *p = reinterpret_cast<const float4 *>(src + (((size_t)dd * H + hh) * W + ww) * 8);
+            const float4 lo = __ldg(p), hi = __ldg(p + 1);
+            const float a[5] = {fmaxf(fmaf(lo.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(lo.y, sc[1], sh[1]), 0.f),
+                                fmaxf(fmaf(lo.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(lo.w, sc[3], sh[3]), 0.f),
+                                fmaxf(fmaf(hi.x, sc[4], sh[4]), 0.f)};
+#pragma unroll
+            for (int ci = 0; ci < 5; ++ci)
+#pragma unroll
+                for (int co = 0; co < 5; ++co) acc[co] = fmaf(a[ci], w_s[tap * 25 + ci * 5 + co], acc[co]);
+        }
+        float4 *o = reinterpret_cast<float4 *>(raw9 + ((size_t)n * vox + v) * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            ssum[c] += acc[c];
+            ssq[c] = fmaf(acc[c], acc[c], ssq[c]);
+        }
+    }
+    block_reduce_atomic<5>(ssum, stats9 + (size_t)n * 5 * 2 + 0, 2);
+    block_reduce_atomic<5>(ssq, stats9 + (size_t)n * 5 * 2 + 1, 2);
+}
+
+// sigmoid(bn(raw9)) -> the cropped interior of every chunk is placed into the
+// (5, Z, Y, X) feature volume (predict.py:89-95): each voxel is written by exactly one chunk.
+__global__ void __launch_bounds__(256)
+place_kernel(const float *__restrict__ raw9, const float *__restrict__ stats9,
+             const float *__restrict__ gamma, const float *__restrict__ beta,
+             const int *__restrict__ starts, const int *__restrict__ crop_lo,
+             const int *__restrict__ crop_hi, float *__restrict__ feats, int Z, int Y, int X, int D,
+             int H, int W) {
+    __shared__ float sc[5], sh[5];
+    const int n = blockIdx.y;
+    const size_t vox = (size_t)D * H * W;
+    if (threadIdx.x < 5)
+        bn_coeffs(stats9 + ((size_t)n * 5 + threadIdx.x) * 2, gamma[threadIdx.x], beta[threadIdx.x],
+                  1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
+    __syncthreads();
+    const int lz = crop_lo[n * 3], ly = crop_lo[n * 3 + 1], lx = crop_lo[n * 3 + 2];
+    const int cd = crop_hi[n * 3] - lz, ch = crop_hi[n * 3 + 1] - ly, cw = crop_hi[n * 3 + 2] - lx;
+    const int z0 = starts[n * 3], y0 = starts[n * 3 + 1], x0 = starts[n * 3 + 2];
+    const size_t total = (size_t)cd * ch * cw;
+    const size_t plane = (size_t)Z * Y * X;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int w = lx + (int)(i % cw);
+        const size_t t = i / cw;
+        const int h = ly + (int)(t % ch);
+        const int d = lz + (int)(t / ch);
+        const float4 *p = reinterpret_cast<const float4 *>(
+            raw9 + ((size_t)n * vox + ((size_t)d * H + h) * W + w) * 8);
+        const float4 lo = __ldg(p), hi = __ldg(p + 1);
+        const float x[5] = {lo.x, lo.y, lo.z, lo.w, hi.x};
+        const size_t o = ((size_t)(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float y = fmaf(x[c], sc[c], sh[c]);
+            feats[c * plane + o] = 1.0f / (1.0f + expf(-y));
+        }
+    }
+}
+
+// ---- weight packing -------------------------------------------------------------
+// nn.Conv3d weight (Cout, Cin, 3,3,3) fp32 -> [tap][cout_pad][cin] fp16 (rows >= Cout zero)
+__global__ void pack_conv_w_kernel(const float *__restrict__ src, __half *__restrict__ dst, int cout,
+                                   int cout_pad, int cin) {
+    const size_t total = (size_t)27 * cout_pad * cin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const size_t t = i / cin;
+        const int co = (int)(t % cout_pad);
+        const int tap = (int)(t / cout_pad);
+        float v = 0.0f;
+        if (co < cout) v = src[((size_t)co * cin + ci) * 27 + tap];
+        dst[i] = __float2half_rn(v);
+    }
+}
+// (Cout, Cin, 27) fp32 -> [tap][cin][cout] fp32 (CUDA-core layers)
+__global__ void pack_conv_w_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int cout,
+                                       int cin) {
+    const int total = 27 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % cout;
+        const int t = i / cout;
+        const int ci = t % cin;
+        const int tap = t / cin;
+        dst[i] = src[((size_t)co * cin + ci) * 27 + tap];
+    }
+}
+__global__ void copy_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// fp16 channels-last [vox][C] of one chunk -> fp32 [C][vox] (debug / parity only)
+__global__ void debug_to_ncdhw_kernel(const void *__restrict__ src, int is_f32, int cstride, int C,
+                                      size_t vox, float *__restrict__ dst) {
+    const size_t total = vox * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = i % vox;
+        const int c = (int)(i / vox);
+        dst[i] = is_f32 ? reinterpret_cast<const float *>(src)[v * cstride + c]
+                        : __half2float(reinterpret_cast<const __half *>(src)[v * cstride + c]);
+    }
+}
+
+}  // namespace isg
