@@ -151,6 +151,19 @@ int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame, const cha
 /* algorithmic FLOPs of one forward over all chunks of the plan (2*MAC of 18 conv + 4 tconv) */
 double isg_unet_plan_flops(const isg_unet_plan *plan);
 
+/* per-launch CUDA-event timing of the forward pass (used by bench.py for the roofline
+ * object): enable, run forwards, synchronise the stream, read.
+ * out[5] = {ms in tcgen05 convolutions, #tcgen05 launches, ms of whole forwards, #forwards,
+ *           algorithmic FLOPs of the tcgen05 convolutions of ONE forward}. */
+int isg_unet_plan_profile(isg_unet_plan *plan, int enable);
+int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out);
+
+/* ---- label bookkeeping for frame-sharded time series ------------------------
+ * labels[i] += offset for every non-zero label (global label ids across frames:
+ * an addition of this implementation, the reference restarts at 1 in every frame,
+ * watershed.py:61-62). */
+int isg_add_label_offset(uint32_t *labels, int64_t n, uint32_t offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

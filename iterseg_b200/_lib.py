@@ -41,6 +41,9 @@ SIGNATURES = {
     'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),
     'isg_unet_debug_activation': (_i32, [_vp, _vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
     'isg_unet_plan_flops': (_c.c_double, [_vp]),
+    'isg_unet_plan_profile': (_i32, [_vp, _i32]),
+    'isg_unet_plan_profile_read': (_i32, [_vp, _vp]),
+    'isg_add_label_offset': (_i32, [_vp, _i64, _c.c_uint32, _vp]),
 }
 
 _lib = None

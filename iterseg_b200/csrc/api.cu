@@ -37,3 +37,22 @@ extern "C" int isg_device_check(void) {
     }
     return ISG_OK;
 }
+
+namespace isg {
+__global__ void __launch_bounds__(256)
+add_label_offset_kernel(uint32_t *labels, uint64_t n, uint32_t offset) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t l = labels[i];
+        if (l) labels[i] = l + offset;
+    }
+}
+}  // namespace isg
+
+extern "C" int isg_add_label_offset(uint32_t *labels, int64_t n, uint32_t offset, void *stream) {
+    ISG_REQUIRE(labels && n >= 0, ISG_ERR_ARG, "isg_add_label_offset: bad argument");
+    if (n == 0 || offset == 0) return ISG_OK;
+    isg::add_label_offset_kernel<<<isg::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(labels, (uint64_t)n, offset);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}

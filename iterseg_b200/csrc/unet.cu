@@ -129,12 +129,18 @@ struct isg_unet_plan {
     int *starts, *crop_lo, *crop_hi;
     __half *raw[5], *act[5], *skip[4], *pooled[5], *up[4];
     float *raw8, *raw9;
-    float *stats[18];
-    float *stats_all;
+    unsigned long long *stats[18];
+    unsigned long long *stats_all;
     size_t stats_bytes;
     isg::TcLayer tc[18];
     int base_off_mode;
     double flops;
+    double tc_flops;              // algorithmic FLOPs of the 16 tensor-core convolutions
+    // optional per-launch CUDA-event timing (bench roofline): kind 0 = tcgen05 conv, 1 = other
+    int profiling;
+    std::vector<cudaEvent_t> ev;  // pairs (start, stop)
+    std::vector<int> ev_kind;
+    size_t ev_used;
 };
 
 namespace isg {
@@ -178,10 +184,10 @@ static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
     p->raw9 = cv.take<float>(vox(0) * 8);
     size_t floats = 0;
     for (int i = 0; i < 18; ++i) floats += (size_t)N * cout_pad(i) * 2;
-    p->stats_all = cv.take<float>(floats);
-    p->stats_bytes = floats * sizeof(float);
+    p->stats_all = cv.take<unsigned long long>(floats);
+    p->stats_bytes = floats * sizeof(unsigned long long);
     if (p->stats_all) {
-        float *s = p->stats_all;
+        unsigned long long *s = p->stats_all;
         for (int i = 0; i < 18; ++i) {
             p->stats[i] = s;
             s += (size_t)N * cout_pad(i) * 2;
@@ -248,6 +254,30 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     return true;
 }
 
+struct ProfScope {
+    isg_unet_plan *p;
+    cudaStream_t st;
+    size_t slot;
+    ProfScope(isg_unet_plan *plan, int kind, cudaStream_t s) : p(plan), st(s), slot((size_t)-1) {
+        if (!p->profiling) return;
+        if (p->ev_used + 2 > p->ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            p->ev.push_back(a);
+            p->ev.push_back(b);
+            p->ev_kind.push_back(kind);
+        }
+        slot = p->ev_used;
+        p->ev_kind[slot / 2] = kind;
+        p->ev_used += 2;
+        cudaEventRecord(p->ev[slot], st);
+    }
+    ~ProfScope() {
+        if (slot != (size_t)-1) cudaEventRecord(p->ev[slot + 1], st);
+    }
+};
+
 static int launch_tc(const TcLayer &t, cudaStream_t st) {
     if (t.cblk == 64) {
         ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
@@ -271,6 +301,11 @@ static inline dim3 egrid(size_t work, int N) {
 // run the network up to and including conv `stop` (17 = everything incl. placement)
 static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop, cudaStream_t st) {
     const int N = p->N;
+    auto run_tc = [&](int i) {
+        ProfScope ps(p, 0, st);
+        return launch_tc(p->tc[i], st);
+    };
+    ProfScope whole(p, 1, st);
     const unsigned char *pk = p->packed;
     const PackLayout &L = p->L;
     auto G = [&](int i) { return reinterpret_cast<const float *>(pk + L.gamma[i]); };
@@ -288,14 +323,14 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     for (int l = 0; l < 5; ++l) {
         const int i0 = 2 * l, i1 = 2 * l + 1;
         if (l > 0) {
-            int rc = launch_tc(p->tc[i0], st);
+            int rc = run_tc(i0);
             if (rc) return rc;
             if (stop == i0) return ISG_OK;
         }
         bn_relu_kernel<<<egrid(vox(l) * CH[l] / 8, N), 256, 0, st>>>(p->raw[l], p->act[l], p->stats[i0],
                                                                      G(i0), B(i0), CH[l], vox(l));
         ISG_LAUNCHED();
-        int rc = launch_tc(p->tc[i1], st);
+        int rc = run_tc(i1);
         if (rc) return rc;
         if (stop == i1) return ISG_OK;
         if (l < 4) {
@@ -330,7 +365,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
         ISG_LAUNCHED();
         const int i0 = 10 + 2 * u, i1 = i0 + 1;
-        int rc = launch_tc(p->tc[i0], st);          // reads [up, skip] of level lf
+        int rc = run_tc(i0);                        // reads [up, skip] of level lf
         if (rc) return rc;
         if (stop == i0) return ISG_OK;
         if (u < 3) {
@@ -338,7 +373,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             bn_relu_kernel<<<egrid(vox(lf) * Cm / 8, N), 256, 0, st>>>(p->raw[lf], p->act[lf], p->stats[i0],
                                                                        G(i0), B(i0), Cm, vox(lf));
             ISG_LAUNCHED();
-            rc = launch_tc(p->tc[i1], st);
+            rc = run_tc(i1);
             if (rc) return rc;
             if (stop == i1) return ISG_OK;
         }
@@ -401,7 +436,6 @@ extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, 
 extern "C" size_t isg_unet_workspace_bytes(int n_chunks, int cz, int cy, int cx) {
     if (n_chunks <= 0) return 0;
     isg_unet_plan p;
-    memset(&p, 0, sizeof(p));
     p.N = n_chunks;
     if (!level_dims(&p, cz, cy, cx)) return 0;
     Carver cv(nullptr, 0);
@@ -423,13 +457,18 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
         return nullptr;
     }
     isg_unet_plan *p = new isg_unet_plan();
-    memset((void *)p, 0, sizeof(*p));
+    p->profiling = 0;
+    p->ev_used = 0;
     p->N = n_chunks;
     p->Z = (int)z; p->Y = (int)y; p->X = (int)x;
     p->packed = (const unsigned char *)packed_weights;
     p->L = pack_layout();
+    // Measured on B200: the UMMA operand fetch swizzles on absolute shared-memory address
+    // bits, so a descriptor whose start address is advanced by whole rows needs base_offset 0
+    // (profiles/r01_notes.md).  ISG_CONV_BASE_OFFSET=1 re-enables the (wrong) alternative for
+    // diagnosis only.
     const char *bm = getenv("ISG_CONV_BASE_OFFSET");
-    p->base_off_mode = bm ? atoi(bm) : 1;
+    p->base_off_mode = bm ? atoi(bm) : 0;
     if (!level_dims(p, cz, cy, cx)) {
         set_error("chunk shape (%d,%d,%d) is not valid for this U-Net: z must be even and y/x must survive "
                   "four poolings and the decoder crops (e.g. 10,256,256)", cz, cy, cx);
@@ -477,11 +516,14 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
         delete p;
         return nullptr;
     }
-    double macs = 0;
+    double macs = 0, tc_macs = 0;
     for (int i = 0; i < 18; ++i) {
         const int l = CONVS[i].level;
-        macs += 27.0 * CONVS[i].cin * CONVS[i].cout * p->D[l] * p->H[l] * p->W[l];
+        const double m = 27.0 * CONVS[i].cin * CONVS[i].cout * p->D[l] * p->H[l] * p->W[l];
+        macs += m;
+        if (is_tc(i)) tc_macs += m;
     }
+    p->tc_flops = 2.0 * tc_macs * n_chunks;
     for (int u = 0; u < 4; ++u) {
         const int lc = 4 - u;
         macs += (double)UP_C[u] * UP_KZ[u] * 4 * p->D[lc] * p->H[lc] * p->W[lc];
@@ -490,7 +532,36 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
     return p;
 }
 
-extern "C" void isg_unet_plan_destroy(isg_unet_plan *plan) { delete plan; }
+extern "C" void isg_unet_plan_destroy(isg_unet_plan *plan) {
+    if (!plan) return;
+    for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    delete plan;
+}
+
+extern "C" int isg_unet_plan_profile(isg_unet_plan *plan, int enable) {
+    ISG_REQUIRE(plan, ISG_ERR_ARG, "isg_unet_plan_profile: null plan");
+    plan->profiling = enable ? 1 : 0;
+    plan->ev_used = 0;
+    return ISG_OK;
+}
+
+// Sum the event-timed launches recorded since profiling was (re-)enabled.  The caller
+// must have synchronised the stream.  out[0] = ms in tcgen05 convolutions, out[1] = number
+// of tcgen05 conv launches, out[2] = ms of whole forward passes, out[3] = number of
+// forward passes, out[4] = algorithmic FLOPs of the tcgen05 convolutions of one forward.
+extern "C" int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out) {
+    ISG_REQUIRE(plan && out, ISG_ERR_ARG, "isg_unet_plan_profile_read: null pointer");
+    double tc_ms = 0, all_ms = 0;
+    int n_tc = 0, n_fw = 0;
+    for (size_t s = 0; s + 1 < plan->ev_used; s += 2) {
+        float ms = 0;
+        ISG_CUDA(cudaEventElapsedTime(&ms, plan->ev[s], plan->ev[s + 1]));
+        if (plan->ev_kind[s / 2] == 0) { tc_ms += ms; ++n_tc; }
+        else { all_ms += ms; ++n_fw; }
+    }
+    out[0] = tc_ms; out[1] = n_tc; out[2] = all_ms; out[3] = n_fw; out[4] = plan->tc_flops;
+    return ISG_OK;
+}
 
 extern "C" double isg_unet_plan_flops(const isg_unet_plan *plan) { return plan ? plan->flops : 0.0; }
 

@@ -41,12 +41,14 @@ struct ConvGeom {
     int b_stage_bytes;           // cout * CBLK * 2
     int n_b_stages;
     int out_mode;                // 0: fp16 [vox][cout]   1: fp32 [vox][8] (first 8 columns)
-    int base_off_mode;           // 1: descriptor base_offset = (addr >> 7) & 7   0: always 0
+    int base_off_mode;           // 0 (correct on B200): descriptor base_offset field = 0;  1: (addr >> 7) & 7
     void *out;
-    float *stats;                // [N][cout][2] (sum, sum of squares), fp32 atomics
+    unsigned long long *stats;   // [N][cout][2] (sum, sum of squares) as 2^-24 fixed point:
+                                 // integer atomics are order-independent -> reproducible
 };
 
 static constexpr int CONV_THREADS = 256;
+static constexpr float STAT_SCALE = 16777216.0f;      // 2^24
 static constexpr int CONV_SLACK = 4096;      // garbage rows the last taps of invalid rows touch
 
 __host__ __device__ inline size_t conv_smem_bytes(const ConvGeom &g) {
@@ -185,9 +187,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===================== epilogue =====================
         const int ew = warp - 4;                     // TMEM lanes 32*ew .. 32*ew+31
         float *st = stat_t + ew * (32 * 33);
-        float csum[8], csq[8];
+        long long csum[8], csq[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) csum[i] = csq[i] = 0.0f;
+        for (int i = 0; i < 8; ++i) csum[i] = csq[i] = 0;
         int cur_n = -1;
         uint32_t tcount = 0;
         const int row = ew * 32 + lane;
@@ -198,10 +200,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int i = 0; i < 8; ++i) {
                 const int c = i * 32 + lane;
                 if (i * 32 < g.cout && c < g.cout) {
-                    atomicAdd(g.stats + ((size_t)n * g.cout + c) * 2 + 0, csum[i]);
-                    atomicAdd(g.stats + ((size_t)n * g.cout + c) * 2 + 1, csq[i]);
+                    atomicAdd(g.stats + ((size_t)n * g.cout + c) * 2 + 0, (unsigned long long)csum[i]);
+                    atomicAdd(g.stats + ((size_t)n * g.cout + c) * 2 + 1, (unsigned long long)csq[i]);
                 }
-                csum[i] = csq[i] = 0.0f;
+                csum[i] = csq[i] = 0;
             }
         };
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcount) {
@@ -254,8 +256,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             q2 = fmaf(x, x, q2);
                         }
                         __syncwarp();
-                        csum[i] += s;
-                        csq[i] += q2;
+                        csum[i] += __float2ll_rn(s * STAT_SCALE);
+                        csq[i] += __float2ll_rn(q2 * STAT_SCALE);
                     }
                 }
             } else {
@@ -282,8 +284,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
                 __syncwarp();
-                csum[0] += s;
-                csq[0] += q2;
+                csum[0] += __float2ll_rn(s * STAT_SCALE);
+                csq[0] += __float2ll_rn(q2 * STAT_SCALE);
             }
             tc_fence_before();
             __syncwarp();

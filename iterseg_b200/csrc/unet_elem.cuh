@@ -17,13 +17,15 @@ namespace isg {
 static constexpr float BN_EPS = 1e-5f;
 
 // BatchNorm3d in training mode: batch statistics (biased variance) of ONE chunk.
-__device__ __forceinline__ void bn_coeffs(const float *stats_c, float gamma, float beta,
+// stats_c = (sum, sum of squares) in 2^-24 fixed point (see STAT_SCALE in unet_conv.cuh).
+__device__ __forceinline__ void bn_coeffs(const unsigned long long *stats_c, float gamma, float beta,
                                           float inv_count, float &scale, float &shift) {
-    const float mean = stats_c[0] * inv_count;
-    const float var = fmaxf(stats_c[1] * inv_count - mean * mean, 0.0f);
-    const float inv = 1.0f / sqrtf(var + BN_EPS);
+    const double k = (double)inv_count / 16777216.0;
+    const double mean = (double)(long long)stats_c[0] * k;
+    const double var = fmax((double)(long long)stats_c[1] * k - mean * mean, 0.0);
+    const float inv = 1.0f / sqrtf((float)var + BN_EPS);
     scale = gamma * inv;
-    shift = beta - mean * scale;
+    shift = beta - (float)mean * scale;
 }
 
 __device__ __forceinline__ void load8h(const __half *p, float (&v)[8]) {
@@ -45,7 +47,7 @@ __device__ __forceinline__ void store8h(__half *p, const float (&v)[8]) {
 }
 
 // shared scale/shift table for the chunk this block works on (C <= 256)
-__device__ __forceinline__ void bn_table(float *s_scale, float *s_shift, const float *stats,
+__device__ __forceinline__ void bn_table(float *s_scale, float *s_shift, const unsigned long long *stats,
                                          const float *gamma, const float *beta, int C, int n,
                                          float inv_count) {
     for (int c = threadIdx.x; c < C; c += blockDim.x)
@@ -55,7 +57,7 @@ __device__ __forceinline__ void bn_table(float *s_scale, float *s_shift, const f
 
 // raw -> relu(bn(raw)), same shape.  grid = (blocks, N)
 __global__ void __launch_bounds__(256)
-bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const float *__restrict__ stats,
+bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const unsigned long long *__restrict__ stats,
                const float *__restrict__ gamma, const float *__restrict__ beta, int C, size_t vox) {
     __shared__ float s_scale[256], s_shift[256];
     const int n = blockIdx.y;
@@ -81,7 +83,7 @@ bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const f
 template <int PZ>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
-                    __half *__restrict__ pooled, const float *__restrict__ stats,
+                    __half *__restrict__ pooled, const unsigned long long *__restrict__ stats,
                     const float *__restrict__ gamma, const float *__restrict__ beta, int C, int D,
                     int H, int W, int Dc, int Hc, int Wc) {
     __shared__ float s_scale[256], s_shift[256];
@@ -138,7 +140,7 @@ bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
 template <int KZ>
 __global__ void __launch_bounds__(256)
 bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
-                  const float *__restrict__ stats, const float *__restrict__ gamma,
+                  const unsigned long long *__restrict__ stats, const float *__restrict__ gamma,
                   const float *__restrict__ beta, const float *__restrict__ wgt,
                   const float *__restrict__ bias, int C, int Dc, int Hc, int Wc, int Df, int Hf,
                   int Wf, int off) {
@@ -184,7 +186,7 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
 
 // block-wide reduction of NV per-thread partial sums -> atomicAdd into dst[i*stride]
 template <int NV>
-__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float *dst, int stride) {
+__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], unsigned long long *dst, int stride) {
     __shared__ float red[8][NV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -199,7 +201,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float *dst, 
     for (int i = threadIdx.x; i < NV; i += blockDim.x) {
         float x = 0.0f;
         for (int w = 0; w < nw; ++w) x += red[w][i];
-        atomicAdd(dst + (size_t)i * stride, x);
+        atomicAdd(dst + (size_t)i * stride, (unsigned long long)__float2ll_rn(x * 16777216.0f));
     }
     __syncthreads();
 }
@@ -210,7 +212,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float *dst, 
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *__restrict__ starts,
                const float *__restrict__ wgt /* [27][32] */, __half *__restrict__ raw,
-               float *__restrict__ stats, int D, int H, int W) {
+               unsigned long long *__restrict__ stats, int D, int H, int W) {
     __shared__ float w_s[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) w_s[i] = wgt[i];
     __syncthreads();
@@ -260,10 +262,10 @@ conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *
 // fp32 [vox][8] output of c8_0.conv0 (stats8 has 16 columns per chunk), zero outside the
 // chunk.  Output raw9 fp32 [vox][8] + statistics [N][5][2].   grid = (blocks, N)
 __global__ void __launch_bounds__(256)
-conv_out_kernel(const float *__restrict__ raw8, const float *__restrict__ stats8,
+conv_out_kernel(const float *__restrict__ raw8, const unsigned long long *__restrict__ stats8,
                 const float *__restrict__ gamma8, const float *__restrict__ beta8,
                 const float *__restrict__ wgt /* [27][5 in][5 out] */, float *__restrict__ raw9,
-                float *__restrict__ stats9, int D, int H, int W) {
+                unsigned long long *__restrict__ stats9, int D, int H, int W) {
     __shared__ float w_s[27 * 25];
     __shared__ float sc[5], sh[5];
     const int n = blockIdx.y;
@@ -314,7 +316,7 @@ conv_out_kernel(const float *__restrict__ raw8, const float *__restrict__ stats8
 // sigmoid(bn(raw9)) -> the cropped interior of every chunk is placed into the
 // (5, Z, Y, X) feature volume (predict.py:89-95): each voxel is written by exactly one chunk.
 __global__ void __launch_bounds__(256)
-place_kernel(const float *__restrict__ raw9, const float *__restrict__ stats9,
+place_kernel(const float *__restrict__ raw9, const unsigned long long *__restrict__ stats9,
              const float *__restrict__ gamma, const float *__restrict__ beta,
              const int *__restrict__ starts, const int *__restrict__ crop_lo,
              const int *__restrict__ crop_hi, float *__restrict__ feats, int Z, int Y, int X, int D,

@@ -1,0 +1,243 @@
+"""Segmenter registry + per-frame driver: the reference's segmentation module.
+
+Mirrors src/iterseg/segmentation.py for the affinity U-Net watershed path:
+`affinity_unet_watershed` (:24-73), `affinity_watershed_prep_config` (:80-135),
+`a_w_output_volume` (:138-140), `affinity_watershed_for_chunks` (:147-195),
+`read_config_json` (:687-690), `segmentation_wrapper` (:700-830),
+`segmentation_loop` (:833-882), `segment_single_volume` (:885-900),
+`remove_sum_zero_slices` (:903-916) and the `segmenters` registry (:924-930).
+
+What differs from the reference, on purpose:
+* one frame goes host -> device once, the feature volume never leaves the
+  device (the reference moves 2.6 MB in / 13.1 MB out per chunk, predict.py:119-123),
+  labels come back once; `output_volume` (the reference's host scratch, zeroed at
+  the end of every frame, :195) is left untouched -- i.e. zero, as the reference
+  leaves it;
+* without napari the frame loop runs inline (the reference uses a napari
+  thread_worker unless debug=True, :808-828);
+* the `.json` config branch accepts what the reference's documentation promises
+  (`{"unet": "default" | "labels layer" | path}`) instead of raising
+  UnboundLocalError (:98-107).
+"""
+import json
+import os
+import pathlib
+from typing import Callable, Union
+
+import numpy as np
+import torch
+
+from . import _io, _lib
+from . import watershed as ws
+from .predict import (load_unet, predict_chunk_feature_map, predict_frame_device,  # noqa: F401
+                      process_chunks)
+from . import unet as unet_mod
+
+
+# ------------------------
+# Affinity U-net Watershed
+# ------------------------
+
+def affinity_unet_watershed(napari_viewer, input_volume_layer, save_dir: Union[str, None] = None,
+                            name: str = 'my-segmentation',
+                            unet_or_config_file: Union[str, None] = None,
+                            layer_reference: Union[str, None] = None,
+                            chunk_size: Union[tuple, None] = (10, 256, 256),
+                            margin: Union[tuple, None] = (1, 64, 64), debug: bool = False):
+    """Same arguments as the reference (segmentation.py:24-73).  Returns the output labels
+    layer (the reference's wrapper computes it but drops the return value)."""
+    return segmentation_wrapper(affinity_watershed_for_chunks, affinity_watershed_prep_config,
+                                napari_viewer, input_volume_layer, save_dir, name,
+                                unet_or_config_file, layer_reference, chunk_size, margin, debug)
+
+
+def affinity_watershed_prep_config(input_volume_layer, unet_or_config_file, reference_layer):
+    unet = None
+    affinities_extent = 1
+    if isinstance(unet_or_config_file, pathlib.PurePath):
+        unet_or_config_file = str(unet_or_config_file)
+    if isinstance(unet_or_config_file, str):
+        if unet_or_config_file.endswith('.json'):
+            config = read_config_json(unet_or_config_file)
+            unet = config.get('unet')
+            if config.get('affinities_extent') is not None:
+                affinities_extent = int(config['affinities_extent'])
+            if unet == 'labels layer':
+                unet = reference_layer.metadata['unet']
+            if unet == 'default':
+                unet = None
+        elif unet_or_config_file.endswith('.pt') or unet_or_config_file.endswith('.pth'):
+            unet = unet_or_config_file
+        else:
+            raise ValueError('Please provide a valid path to a pytorch unet - must end with .pt or .pth')
+    elif unet_or_config_file is not None:
+        raise ValueError('Please provide a valid path to a pytorch unet - must end with .pt or .pth')
+    if unet is not None:
+        if isinstance(unet, str):
+            m = f'There was not file at the provided location: {unet}\nMake sure a pytorch unet lives here...'
+            assert os.path.exists(unet), m
+            assert unet.endswith('.pt') or unet.endswith('.pth')
+        else:
+            raise ValueError('Please provide a valid path to a pytorch unet - must end with .pt or .pth')
+    if affinities_extent != 1:
+        raise NotImplementedError('only affinities_extent = 1 (5 prediction channels) is supported')
+    num_pred_channels = 3 * affinities_extent + 2
+    output_volume = a_w_output_volume(input_volume_layer.data, num_pred_channels)
+    unet = load_unet(unet)
+    return {'unet': unet, 'output_volume': output_volume}
+
+
+def a_w_output_volume(data, num_pred_channels, **kwargs):
+    return np.zeros((num_pred_channels,) + tuple(data.shape[-3:]), dtype=np.float32)
+
+
+def affinity_watershed_for_chunks(input_volume, current_output, chunk_size, margin, unet=None,
+                                  output_volume=None, **kwargs):
+    """The processing function of the plug-in protocol (segmentation.py:147-195):
+    writes the labels of one frame IN PLACE into `current_output`, the padded
+    (Z+2,Y+2,X+2) uint32 array the driver allocates (:890-895)."""
+    if output_volume is None:
+        raise ValueError('output_volume must not be None. Please ensure the output volume is supplied in the config dict')
+    if unet is None:
+        raise ValueError('unet must not be none. Please ensure a unet was loaded and added to the config dict in the config function')
+    if not isinstance(unet, unet_mod.UNet):
+        raise TypeError('unet must be an iterseg_b200.unet.UNet (use iterseg_b200.predict.load_unet)')
+    _lib.require_device()
+    dev = unet.device
+    vol = input_volume if isinstance(input_volume, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(input_volume, dtype=np.float32))
+    frame = vol.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    feats = predict_frame_device(unet, frame, tuple(int(c) for c in chunk_size), margin)
+    shape_p = tuple(int(s) + 2 for s in frame.shape)
+    out_is_dev = isinstance(current_output, torch.Tensor) and current_output.is_cuda
+    labels = current_output.view(shape_p) if out_is_dev else \
+        torch.zeros(shape_p, dtype=torch.int32, device=dev)
+    ws.segment_features_device(feats, labels, affinities_channels=(0, 1, 2),
+                               thresholding_channel=3, centroids_channel=4)
+    if not out_is_dev:
+        direct = (isinstance(current_output, np.ndarray) and current_output.flags.c_contiguous
+                  and current_output.dtype in (np.uint32, np.int32)
+                  and current_output.size == labels.numel())
+        if direct:                                 # one D2H copy straight into the caller's array
+            torch.from_numpy(current_output.reshape(-1).view(np.int32)).copy_(labels.view(-1))
+        else:
+            flat = current_output.reshape(-1)      # a view, like current_output.ravel() in :194
+            flat[...] = labels.cpu().numpy().view(np.uint32).reshape(-1).astype(flat.dtype, copy=False)
+
+
+# ---------------
+# Common funcions
+# ---------------
+
+def read_config_json(path_to_json):
+    with open(path_to_json, 'r') as f:
+        return json.load(f)
+
+
+def segmentation_wrapper(processing_function: Callable, config_prep_function: Callable,
+                         napari_viewer, input_volume_layer, save_dir: Union[str, None], name: str,
+                         network_or_config_file: Union[str, None],
+                         layer_reference: Union[str, None], chunk_size: tuple, margin: tuple,
+                         debug: bool = False):
+    viewer = napari_viewer
+    config = config_prep_function(input_volume_layer, network_or_config_file, layer_reference)
+    if config is None:
+        config = {}
+    save_path = None
+    if save_dir is not None and not debug:
+        save_path = os.path.join(str(save_dir), name + '.ome.zarr')
+    data = input_volume_layer.data
+    shape = data.shape
+    scale = input_volume_layer.scale
+    translate = input_volume_layer.translate
+    layer_meta = {'scale': scale, 'translate': translate, 'name': name}
+    if save_path is not None:
+        output_labels = _io.save_labels_to_ome(save_path, layer_meta=layer_meta, shape=shape,
+                                               chunks=chunk_size, dtype=np.int32)
+    else:
+        output_labels = _io.zeros(shape=shape, chunks=chunk_size, dtype=np.int32)
+    output_layer = viewer.add_labels(output_labels, name=name, scale=scale, translate=translate)
+
+    def handle_yields(yielded_val):
+        viewer.dims.current_step = (yielded_val, 0, 0, 0)
+        print(f"Segmented t = {yielded_val}")
+
+    worker_factory = None
+    if not debug:
+        try:                                                  # the reference's threaded mode
+            from napari.qt import thread_worker
+            worker_factory = thread_worker(
+                segmentation_loop, progress={'total': data.shape[0], 'desc': 'thread-progress'},
+                connect={'yielded': handle_yields, 'errored': _raise})
+        except Exception:
+            worker_factory = None
+    if worker_factory is not None:
+        worker_factory(viewer, data, chunk_size, margin, output_labels, processing_function, config)
+    else:
+        for t in segmentation_loop(viewer, data, chunk_size, margin, output_labels,
+                                   processing_function, config):
+            if debug:
+                print(f'Segmented frame {t}')
+            else:
+                handle_yields(t)
+    return output_layer
+
+
+def _raise(err):
+    raise err
+
+
+def segmentation_loop(viewer, data, chunk_size, margin, output_labels, processing_function, config):
+    """One 3-D frame at a time; yields the time point when done (segmentation.py:833-882),
+    including the warm restart: frames whose output is already non-zero are skipped."""
+    ndim = data.ndim
+    if ndim == 3:
+        output = segment_single_volume(np.asarray(data).astype(np.float32), chunk_size, config,
+                                       margin, processing_function)
+        output_labels[...] = output
+        yield 0
+        return
+    for t in range(data.shape[0]):
+        if np.any(output_labels[t]):
+            continue
+        input_volume = np.asarray(data[t]).astype(np.float32)
+        current_output = segment_single_volume(input_volume, chunk_size, config, margin,
+                                               processing_function)
+        output_labels[t, ...] = current_output
+        yield t
+
+
+def segment_single_volume(input_volume, chunk_size, config, margin, processing_function):
+    if input_volume.min() == 0:
+        input_volume = remove_sum_zero_slices(input_volume)
+    input_volume /= np.max(input_volume)
+    current_output = np.zeros(tuple(s + 2 for s in input_volume.shape), dtype=np.uint32)
+    crop = (slice(1, -1),) * current_output.ndim
+    processing_function(input_volume, current_output, chunk_size, margin, **config)
+    return current_output[crop]
+
+
+def remove_sum_zero_slices(input_volume):
+    for ax_i in range(input_volume.ndim):
+        keep = [i for i in range(input_volume.shape[ax_i])
+                if np.take(input_volume, i, axis=ax_i).sum() != 0]
+        input_volume = np.take(input_volume, keep, axis=ax_i)
+    return input_volume
+
+
+# ------------------
+# DoG Blob Watershed
+# ------------------
+
+def dog_blob_watershed(napari_viewer, input_volume_layer, save_dir=None, name='labels-prediction',
+                       config_file=None, layer_reference=None, chunk_size=(10, 256, 256),
+                       margin=(1, 64, 64), debug=False):
+    """Registered for interface parity (segmentation.py:548-589); the DoG blob path is a
+    later row of the scope table and is not built yet."""
+    raise NotImplementedError('DoG-blob-watershed is not implemented in iterseg_b200 yet')
+
+
+segmenters = {
+    'affinity-unet-watershed': affinity_unet_watershed,
+    'DoG-blob-watershed': dog_blob_watershed,
+}

@@ -106,3 +106,86 @@ def analytic_features(labels, seed=0, noise=0.01):
         feats += rng.normal(0.0, noise, feats.shape).astype(np.float32)
     np.clip(feats, 1e-4, 1.0, out=feats)
     return feats
+
+
+def structured_state_dict(seed=0, noise=0.25):
+    """A deterministic network file (the reference's state_dict format, train.py:414-420)
+    whose outputs are platelet-shaped WITHOUT training: the bundled network is missing
+    from the reference checkout and there is no network to fetch or time to train one.
+
+    Every convolution gets dense random weights (torch's default scale x `noise`) plus a
+    hand-placed "carrier": channel 0 of every layer copies channel 0 of its input (the first
+    layer applies an in-plane 3x3 box blur; the decoder averages the upsampled and the skip
+    carrier), so a smoothed copy of the
+    intensity image survives the encoder/decoder.  The head maps it to
+      affinities (ch 0-2) = -blur (valleys between touching objects are expensive),
+      mask (ch 3)         = +fine blur,      centre (ch 4) = +coarse blur.
+    FLOPs, shapes and dtypes are those of any UNet(1,5) file; only the values differ.
+    """
+    import torch
+    rng = np.random.default_rng(seed)
+    sd = {}
+    enc = [('c0', 1, 32), ('c1', 32, 64), ('c2', 64, 128), ('c3', 128, 256), ('c4', 256, 256)]
+    dec = [('c5_0', 512, 128), ('c6_0', 256, 64), ('c7_0', 128, 32), ('c8_0', 64, 5)]
+    ups = [('up0', 256, (2, 2, 2)), ('up1', 128, (1, 2, 2)), ('up2', 64, (1, 2, 2)), ('up3', 32, (1, 2, 2))]
+
+    def conv(prefix, cin, cout, carriers, blur=False):
+        b = noise / np.sqrt(cin * 27)
+        w = rng.uniform(-b, b, (cout, cin, 3, 3, 3)).astype(np.float32)
+        for co, ci, gain in carriers:
+            if blur:
+                w[co, ci, 1] += np.float32(gain / 9.0)      # in-plane 3x3 box blur
+            else:
+                w[co, ci, 1, 1, 1] += np.float32(gain)      # identity
+        sd[prefix + '.weight'] = torch.from_numpy(w)
+        sd[prefix + '.bias'] = torch.zeros(cout)
+
+    def bn(prefix, c, beta0=1.5):
+        g = rng.uniform(0.8, 1.2, c).astype(np.float32)
+        be = rng.uniform(-0.2, 0.2, c).astype(np.float32)
+        g[0], be[0] = 1.0, beta0
+        sd[prefix + '.weight'] = torch.from_numpy(g)
+        sd[prefix + '.bias'] = torch.from_numpy(be)
+        sd[prefix + '.running_mean'] = torch.zeros(c)
+        sd[prefix + '.running_var'] = torch.ones(c)
+        sd[prefix + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    for name, cin, cout in enc:
+        conv(name + '.conv0', cin, cout, [(0, 0, 1.0)], blur=(name == 'c0'))
+        conv(name + '.conv1', cout, cout, [(0, 0, 1.0)])
+        bn(name + '.batch0', cout)
+        bn(name + '.batch1', cout)
+    for name, cin, cout in dec:
+        half = cin // 2                      # concat = [upsampled (0..half), skip (half..)]
+        if name != 'c8_0':
+            conv(name + '.conv0', cin, cout, [(0, 0, 0.5), (0, half, 0.5)])
+            conv(name + '.conv1', cout, cout, [(0, 0, 1.0)])
+            bn(name + '.batch0', cout)
+            bn(name + '.batch1', cout)
+        else:
+            # head: ch0-2 = -fine, ch3 = +fine, ch4 = +coarse
+            conv(name + '.conv0', cin, cout,
+                 [(0, half, -1.0), (1, half, -1.0), (2, half, -1.0), (3, half, 1.0), (4, 0, 1.0)])
+            conv(name + '.conv1', cout, cout, [(k, k, 1.0) for k in range(5)])
+            for i in (0, 1):
+                sd[f'{name}.batch{i}.weight'] = torch.ones(cout)
+                sd[f'{name}.batch{i}.bias'] = torch.full((cout,), 1.0 if i == 0 else 0.0)
+                sd[f'{name}.batch{i}.running_mean'] = torch.zeros(cout)
+                sd[f'{name}.batch{i}.running_var'] = torch.ones(cout)
+                sd[f'{name}.batch{i}.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+    # fix the key order of c8_0 to conv0, conv1, batch0, batch1 (state_dict order)
+    ordered = {}
+    for name, _, _ in enc + dec:
+        for k in ('conv0.weight', 'conv0.bias', 'conv1.weight', 'conv1.bias'):
+            ordered[f'{name}.{k}'] = sd[f'{name}.{k}']
+        for i in (0, 1):
+            for k in ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked'):
+                ordered[f'{name}.batch{i}.{k}'] = sd[f'{name}.batch{i}.{k}']
+    for name, c, k in ups:
+        w = rng.uniform(-1, 1, (c, 1) + k).astype(np.float32) * np.float32(0.5 * noise)
+        w[0] = 1.0                            # carrier: nearest-neighbour upsampling
+        bb = rng.uniform(-0.1, 0.1, c).astype(np.float32) * np.float32(noise)
+        bb[0] = 0.0
+        ordered[name + '.weight'] = torch.from_numpy(w)
+        ordered[name + '.bias'] = torch.from_numpy(bb)
+    return ordered

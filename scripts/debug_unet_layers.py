@@ -45,7 +45,7 @@ if __name__ == '__main__':
     shapes = [(4, 32, 32)]
     if '--full' in sys.argv:
         shapes.append((10, 256, 256))
-    for m in (1, 0):
+    for m in ((0, 1) if '--modes' in sys.argv else (0,)):
         for s in shapes:
             try:
                 report(s, mode=m)

@@ -1,0 +1,100 @@
+"""GPU parity of the tcgen05 U-Net against the fp32 oracle / golden chunk.
+Tolerance: 1e-2 max-abs on the five sigmoid outputs (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+@pytest.fixture(scope='module')
+def net():
+    from iterseg_b200 import _lib, unet
+    from oracle import unet_ref
+    _lib.require_device()
+    n = unet.UNet()
+    n.load_state_dict(unet_ref.synth_state_dict(0))
+    return n.cuda()
+
+
+def test_golden_small_chunk(net, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'unet_small.npz'))
+    y = net(torch.from_numpy(g['x'])).cpu().numpy()
+    assert y.shape == g['y'].shape
+    assert np.abs(y - g['y']).max() <= TOL
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 48), (6, 64, 32), (10, 96, 160)])
+def test_odd_shapes_vs_oracle(net, shape):
+    from oracle import unet_ref
+    x = np.random.default_rng(sum(shape)).random((1, 1) + shape, dtype=np.float32)
+    want = unet_ref.unet_forward(torch.from_numpy(x), unet_ref.synth_state_dict(0)).numpy()
+    got = net(torch.from_numpy(x)).cpu().numpy()
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_invalid_chunk_shape_raises(net):
+    with pytest.raises(ValueError):
+        net(torch.zeros((1, 1, 5, 64, 64)))
+    with pytest.raises(ValueError):
+        net(torch.zeros((1, 1, 4, 30, 30)))
+
+
+def test_full_chunk_vs_oracle(net):
+    """One (10,256,256) chunk: the configuration every BASELINE config is built from."""
+    from iterseg_b200 import synth
+    from oracle import unet_ref
+    vol = synth.platelet_frame((10, 256, 256), seed=2)
+    want = unet_ref.unet_forward(torch.from_numpy(vol[None, None]), unet_ref.synth_state_dict(0)).numpy()
+    got = net(torch.from_numpy(vol[None, None])).cpu().numpy()
+    err = np.abs(got - want)
+    assert err.max() <= TOL, (err.max(), err.mean())
+
+
+def test_layerwise_raw_outputs(net):
+    from oracle import unet_ref
+    sd = unet_ref.synth_state_dict(0)
+    shape = (4, 32, 32)
+    x = np.random.default_rng(0).random((1, 1) + shape, dtype=np.float32)
+    ref = {}
+    unet_ref.unet_forward(torch.from_numpy(x), sd, hook=lambda k, v: ref.__setitem__(k, v.clone()))
+    frame = torch.from_numpy(x[0, 0]).cuda()
+    zeros = np.zeros((1, 3), np.int32)
+    hi = np.asarray([shape], np.int32)
+    for m in ('c0', 'c1', 'c2', 'c3', 'c4', 'c5_0', 'c6_0', 'c7_0', 'c8_0'):
+        for i in (0, 1):
+            name = f'{m}.conv{i}'
+            got = net.debug_conv_output(frame, shape, zeros, zeros, hi, name).cpu()
+            want = ref[name][0] - sd[name + '.bias'].view(-1, 1, 1, 1)
+            assert float((got - want).abs().max()) <= 0.01 * max(1.0, float(want.abs().max())), name
+
+
+def test_process_chunks_frame_vs_oracle(net):
+    """Chunk grid + crop-and-place + per-chunk statistics: 12x300x300 -> 8 chunks."""
+    from iterseg_b200 import predict, synth
+    from oracle import unet_ref
+    vol = synth.platelet_frame((12, 300, 300), seed=5)
+    want = unet_ref.predict_frame(vol, unet_ref.synth_state_dict(0))
+    out = np.zeros((5, 12, 300, 300), np.float32)
+    predict.process_chunks(vol, (10, 256, 256), out, (1, 64, 64), predict.predict_chunk_feature_map,
+                           config={'unet': net})
+    assert np.abs(out - want).max() <= TOL
+    # the reference's own chunk-by-chunk driver gives the same result as the batched pass
+    out2 = np.zeros_like(out)
+    predict.process_chunks(vol, (10, 256, 256), out2, (1, 64, 64),
+                           lambda v, sl, **kw: predict.predict_chunk_feature_map(v, sl, **kw),
+                           config={'unet': net})
+    assert np.abs(out2 - out).max() <= 1e-4
+
+
+def test_state_dict_roundtrip(tmp_path, net):
+    from iterseg_b200 import predict
+    path = str(tmp_path / 'net.pt')
+    torch.save(net.state_dict(), path)              # the reference's file format (train.py:414-420)
+    u = predict.load_unet(path)
+    x = torch.rand(1, 1, 4, 32, 32)
+    assert torch.equal(u(x), net(x))

@@ -1,0 +1,148 @@
+"""Host-side logic of the package (no GPU): chunk grids, config handling, label store,
+frame sharding with a 2-rank gloo group."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_make_chunks_matches_reference_golden(golden_dir):
+    from iterseg_b200 import predict
+    grids = json.load(open(os.path.join(golden_dir, 'chunk_grids.json')))
+    for key, g in grids.items():
+        shape, chunk, margin = json.loads(key)
+        st, cr = predict.make_chunks(tuple(shape), tuple(chunk), margin if isinstance(margin, int) else tuple(margin))
+        assert [list(map(int, s)) for s in st] == g['starts'], key
+        assert [[list(map(int, ab)) for ab in c] for c in cr] == g['crops'], key
+
+
+def test_make_chunks_rejects_small_arrays():
+    from iterseg_b200 import predict
+    with pytest.raises(ValueError):
+        predict.make_chunks((8, 256, 256), (10, 256, 256), (1, 64, 64))
+
+
+def test_process_chunks_generic_function_provenance(golden_dir):
+    from iterseg_b200 import predict
+    prov = np.load(os.path.join(golden_dir, 'provenance_12x300x300.npz'))['provenance']
+    out = np.zeros((1, 12, 300, 300), np.float32)
+    k = {'i': 0}
+
+    def fake(input_volume, sl, **kw):
+        k['i'] += 1
+        return np.full((1, 1) + input_volume[sl[1:]].shape, k['i'], np.float32)
+
+    predict.process_chunks(np.zeros((12, 300, 300), np.float32), (10, 256, 256), out, (1, 64, 64), fake)
+    assert np.array_equal(out[0].astype(np.uint8), prov)
+
+
+def test_label_store_roundtrip_and_zarr_chunk_rule(tmp_path):
+    from iterseg_b200 import _io
+    meta = {'scale': (1, 4, 1, 1), 'translate': (0, 0, 0, 0), 'name': 'n'}
+    a = _io.save_labels_to_ome(tmp_path / 'x.ome.zarr', layer_meta=meta, shape=(3, 12, 40, 50),
+                               chunks=(2, 5, 16), dtype=np.int32)
+    assert a.chunks == (2, 5, 16, 50)        # zarr v2: missing trailing dims span the axis
+    ref = np.random.default_rng(0).integers(0, 100, (3, 12, 40, 50)).astype(np.int32)
+    assert not np.any(a[1])
+    a[1, ...] = ref[1]
+    a[0] = ref[0]
+    a[2, 3:5] = ref[2, 3:5]
+    assert np.array_equal(a[1], ref[1]) and np.array_equal(a[0], ref[0])
+    assert np.array_equal(a[2, 3:5], ref[2, 3:5]) and not np.any(a[2, 0])
+    # a second handle on the same directory sees the data (it is a real store)
+    b = _io.open_zarr(str(tmp_path / 'x.ome.zarr' / '0'), shape=(3, 12, 40, 50), chunks=(2, 5, 16), dtype=np.int32)
+    assert np.array_equal(np.asarray(b)[:2], ref[:2])
+    attrs = json.load(open(tmp_path / 'x.ome.zarr' / '.zattrs'))
+    assert attrs['multiscales'][0]['datasets'][0]['coordinateTransformations'][1]['type'] == 'translate'
+    with pytest.raises(ValueError):
+        _io.save_labels_to_ome(tmp_path / 'y.ome.zarr', layer_meta=meta)
+
+
+def test_prep_config_errors(tmp_path):
+    from iterseg_b200 import segmentation, viewer
+    layer = viewer.Image(np.zeros((10, 256, 256), np.float32))
+    with pytest.raises(ValueError):
+        segmentation.affinity_watershed_prep_config(layer, 'network.txt', None)
+    with pytest.raises(AssertionError):
+        segmentation.affinity_watershed_prep_config(layer, str(tmp_path / 'missing.pt'), None)
+    assert segmentation.a_w_output_volume(np.zeros((4, 10, 20, 30)), 5).shape == (5, 10, 20, 30)
+    assert set(segmentation.segmenters) == {'affinity-unet-watershed', 'DoG-blob-watershed'}
+
+
+def test_remove_sum_zero_slices():
+    from iterseg_b200 import segmentation
+    x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    x[:, 1, :] = 0
+    x[0] = 0
+    assert segmentation.remove_sum_zero_slices(x).shape == (1, 2, 4)
+
+
+def test_state_dict_keys_match_reference_format():
+    from iterseg_b200 import synth, unet
+    from oracle import unet_ref
+    net = unet.UNet()
+    assert list(net.state_dict()) == list(unet_ref.synth_state_dict(0))
+    net.load_state_dict(synth.structured_state_dict(0))
+    with pytest.raises(NotImplementedError):
+        unet.UNet(in_channels=2)
+
+
+def test_no_device_fails_loudly():
+    import torch
+    from iterseg_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    with pytest.raises(_lib.IsgError):
+        _lib.require_device()
+    from iterseg_b200 import watershed
+    with pytest.raises(_lib.IsgError):
+        watershed.segment_output_image(np.zeros((5, 4, 8, 8), np.float32), (0, 1, 2), 4, 3)
+
+
+def test_frame_sharding_and_offsets():
+    from iterseg_b200 import distributed as d
+    assert d.shard_frames(7, 1, 3) == [1, 4]
+    assert sorted(sum((d.shard_frames(192, r, 8) for r in range(8)), [])) == list(range(192))
+    assert d.exclusive_offsets([3, 0, 5, 2]).tolist() == [0, 3, 3, 8]
+    lab = np.array([0, 1, 2, 0], np.int32)
+    assert d.add_label_offset_host(lab, 10).tolist() == [0, 11, 12, 0]
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from iterseg_b200 import distributed as d
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+T = 7
+mine = d.shard_frames(T, rank, world)
+local = {t: 10 * t + 1 for t in mine}            # pretend frame t holds 10t+1 labels
+counts = d.gather_label_counts(local, T, rank, world)
+assert counts.tolist() == [10 * t + 1 for t in range(T)], counts
+off = d.exclusive_offsets(counts)
+# every rank offsets its own frames; together the ids are globally unique and dense
+out = {}
+for t in mine:
+    lab = np.arange(0, counts[t] + 1).astype(np.int64)
+    out[t] = d.add_label_offset_host(lab, int(off[t]))
+    assert out[t][0] == 0 and out[t][1] == off[t] + 1 and out[t][-1] == off[t] + counts[t]
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_label_count_allgather_two_ranks_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(GLOO_WORKER % {'root': ROOT})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
