@@ -96,10 +96,10 @@ static bool make_act_map(CUtensorMap *m, const void *base, int C, int W, int H, 
                                      C, W, H, D, N, cblk, P, Ht + 2, (int)r);
     return r == CUDA_SUCCESS;
 }
-static bool make_w_map(CUtensorMap *m, const void *base, int cin, int coutp, int cblk) {
+static bool make_w_map(CUtensorMap *m, const void *base, int cin, int coutp, int cblk, int G) {
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)coutp, 27};
     cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)coutp * cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)cblk, (cuuint32_t)coutp, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)cblk, (cuuint32_t)coutp, (cuuint32_t)G};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
                              strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -229,15 +229,29 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     g.nkb1 = c1 / cblk;
     g.a_rows = 3 * (g.Ht + 2) * g.P;
     g.a_stage_bytes = (g.a_rows * cblk * 2 + 1023) & ~1023;
-    g.b_stage_bytes = g.cout * cblk * 2;
-    const long fixed = 1024 + 2L * g.a_stage_bytes + CONV_SLACK + 512 + 4 * 32 * 33 * 4;
-    long nb = (232448 - fixed) / g.b_stage_bytes;
-    if (nb > 12) nb = 12;
-    if (nb < 2) {
+    // B ring: group G taps per stage so that a stage is <= 36 KB (fewer barrier round trips
+    // for the thin layers); A ring: as many stages as still fit (2..4)
+    const int tap_bytes = g.cout * cblk * 2;
+    int G = 1;
+    for (int cand : {27, 9, 3, 1})
+        if (cand * tap_bytes <= 36 * 1024) { G = cand; break; }
+    g.taps_per_b = G;
+    g.b_stage_bytes = G * tap_bytes;
+    const long budget = 232448 - (1024 + CONV_SLACK + 512 + 4 * 32 * 33 * 4);
+    int nb = g.b_stage_bytes >= 24 * 1024 ? 2 : (g.b_stage_bytes >= 12 * 1024 ? 3 : 4);
+    if (27 / G < nb) nb = 27 / G < 2 ? 2 : 27 / G;
+    long na = (budget - (long)nb * g.b_stage_bytes) / g.a_stage_bytes;
+    if (na > 4) na = 4;
+    if (na < 2) {
         set_error("conv %s: shared memory budget exceeded", CONVS[i].name);
         return false;
     }
-    g.n_b_stages = (int)nb;
+    // spend what is left on more B stages
+    long extra = (budget - na * g.a_stage_bytes - (long)nb * g.b_stage_bytes) / g.b_stage_bytes;
+    if (extra > 0) nb += (int)(extra > 4 ? 4 : extra);
+    if (nb > 16) nb = 16;
+    g.n_b_stages = nb;
+    g.n_a_stages = (int)na;
     g.out_mode = out_mode;
     g.base_off_mode = p->base_off_mode;
     g.out = out;
@@ -250,7 +264,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     } else {
         t.tmA1 = t.tmA0;
     }
-    if (!make_w_map(&t.tmB, p->packed + p->L.w[i], cin, g.cout, cblk)) return false;
+    if (!make_w_map(&t.tmB, p->packed + p->L.w[i], cin, g.cout, cblk, g.taps_per_b)) return false;
     return true;
 }
 
@@ -278,16 +292,31 @@ struct ProfScope {
     }
 };
 
-static int launch_tc(const TcLayer &t, cudaStream_t st) {
-    if (t.cblk == 64) {
-        ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
-        conv3d_tc_kernel<64><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
-    } else {
-        ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
-        conv3d_tc_kernel<32><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
-    }
+template <int CBLK, int G>
+static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
+    ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<CBLK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)t.smem));
+    conv3d_tc_kernel<CBLK, G><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
     ISG_LAUNCHED();
     return ISG_OK;
+}
+
+static int launch_tc(const TcLayer &t, cudaStream_t st) {
+    const int G = t.g.taps_per_b;
+    if (t.cblk == 64) {
+        switch (G) {
+            case 27: return launch_tc_inst<64, 27>(t, st);
+            case 9: return launch_tc_inst<64, 9>(t, st);
+            case 3: return launch_tc_inst<64, 3>(t, st);
+            default: return launch_tc_inst<64, 1>(t, st);
+        }
+    }
+    switch (G) {
+        case 27: return launch_tc_inst<32, 27>(t, st);
+        case 9: return launch_tc_inst<32, 9>(t, st);
+        case 3: return launch_tc_inst<32, 3>(t, st);
+        default: return launch_tc_inst<32, 1>(t, st);
+    }
 }
 
 static inline dim3 egrid(size_t work, int N) {

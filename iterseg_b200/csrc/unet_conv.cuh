@@ -38,8 +38,10 @@ struct ConvGeom {
     int nkb0, nkb1;              // channel blocks taken from source 0 / source 1 (concat)
     int a_rows;                  // 3 * (Ht + 2) * P
     int a_stage_bytes;           // a_rows * CBLK * 2 rounded up to 1024
-    int b_stage_bytes;           // cout * CBLK * 2
+    int b_stage_bytes;           // taps_per_b * cout * CBLK * 2
     int n_b_stages;
+    int n_a_stages;              // 2..4
+    int taps_per_b;              // taps per B stage (template parameter G): 1, 3, 9 or 27
     int out_mode;                // 0: fp16 [vox][cout]   1: fp32 [vox][8] (first 8 columns)
     int base_off_mode;           // 0 (correct on B200): descriptor base_offset field = 0;  1: (addr >> 7) & 7
     void *out;
@@ -52,12 +54,12 @@ static constexpr float STAT_SCALE = 16777216.0f;      // 2^24
 static constexpr int CONV_SLACK = 4096;      // garbage rows the last taps of invalid rows touch
 
 __host__ __device__ inline size_t conv_smem_bytes(const ConvGeom &g) {
-    return 1024 /* alignment */ + 2 * (size_t)g.a_stage_bytes +
+    return 1024 /* alignment */ + (size_t)g.n_a_stages * g.a_stage_bytes +
            (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK + 512 /* barriers */ +
            4 * 32 * 33 * sizeof(float);
 }
 
-template <int CBLK>
+template <int CBLK, int G>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvGeom g) {
@@ -69,12 +71,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t pad = ((raw_base + 1023u) & ~1023u) - raw_base;
     uint8_t *base = smem_dyn + pad;
     uint8_t *a_smem = base;
-    uint8_t *b_smem = a_smem + 2 * (size_t)g.a_stage_bytes;
+    uint8_t *b_smem = a_smem + (size_t)g.n_a_stages * g.a_stage_bytes;
     uint8_t *tail = b_smem + (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
-    uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
-    uint64_t *b_full = bars + 8, *b_empty = bars + 8 + 16;          // up to 16 B stages
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8 + 32);
+    uint64_t *a_full = bars, *a_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10;
+    uint64_t *b_full = bars + 12, *b_empty = bars + 12 + 16;        // up to 16 B stages
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12 + 32);
     float *stat_t = reinterpret_cast<float *>(tail + 512);
 
     const int warp = threadIdx.x >> 5;
@@ -87,9 +89,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < g.n_a_stages; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 4);
         }
@@ -112,6 +116,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===================== A producer =====================
         if (lane == 0) {
             uint32_t it = 0;
+            const uint32_t na = (uint32_t)g.n_a_stages;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int wb = t % g.tiles_w; t /= g.tiles_w;
@@ -119,7 +124,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int d = t % g.D;
                 const int n = t / g.D;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+                    const uint32_t s = it % na, ph = (it / na) & 1u;
                     mbar_wait(&a_empty[s], ph ^ 1u);
                     mbar_expect_tx(&a_full[s], (uint32_t)g.a_rows * RB);
                     const bool first = kb < g.nkb0;
@@ -136,7 +141,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t nb = (uint32_t)g.n_b_stages;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb) {
-                    for (int tap = 0; tap < 27; ++tap, ++it) {
+                    for (int tap = 0; tap < 27; tap += G, ++it) {
                         const uint32_t s = it % nb, ph = (it / nb) & 1u;
                         mbar_wait(&b_empty[s], ph ^ 1u);
                         mbar_expect_tx(&b_full[s], (uint32_t)g.b_stage_bytes);
@@ -148,35 +153,49 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One thread issues everything, so the instruction count per MMA is what bounds
+        // small-N layers: descriptors are (constant high word) | (start address >> 4) and
+        // the tap loop is fully unrolled, leaving ~2 integer adds per tcgen05.mma.
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.cout, 0 /* fp16 */);
-            const uint32_t nb = (uint32_t)g.n_b_stages;
+            const uint32_t nb = (uint32_t)g.n_b_stages, na = (uint32_t)g.n_a_stages;
             uint32_t ita = 0, itb = 0, tcount = 0;
-            const int plane_rows = (g.Ht + 2) * g.P;
+            const uint64_t dproto = make_kmajor_desc(0, RB, 0);
+            const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
+            constexpr uint32_t U = RB >> 4;                       // one row in 16-byte units
+            const uint32_t cz = (uint32_t)((g.Ht + 2) * g.P) * U, cy = (uint32_t)g.P * U;
+            const uint32_t b_tap_units = (uint32_t)(g.cout * CBLK * 2) >> 4;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
                 mbar_wait(&acc_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * (uint32_t)g.cout;
                 for (int kb = 0; kb < nkb; ++kb, ++ita) {
-                    const uint32_t s = ita & 1u, ph = (ita >> 1) & 1u;
+                    const uint32_t s = ita % na, ph = (ita / na) & 1u;
                     mbar_wait(&a_full[s], ph);
-                    const uint32_t a_base = smem_u32(a_smem + (size_t)s * g.a_stage_bytes);
-                    for (int tap = 0; tap < 27; ++tap, ++itb) {
-                        const uint32_t bs = itb % nb, bph = (itb / nb) & 1u;
-                        mbar_wait(&b_full[bs], bph);
-                        tc_fence_after();
+                    const uint32_t a_lo = d_lo | (smem_u32(a_smem + (size_t)s * g.a_stage_bytes) >> 4);
+                    uint32_t b_lo = 0, bs = 0;
+#pragma unroll
+                    for (int tap = 0; tap < 27; ++tap) {
+                        if (tap % G == 0) {
+                            bs = itb % nb;
+                            mbar_wait(&b_full[bs], (itb / nb) & 1u);
+                            tc_fence_after();
+                            b_lo = d_lo | (smem_u32(b_smem + (size_t)bs * g.b_stage_bytes) >> 4);
+                        }
                         const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
-                        const uint32_t a_addr = a_base + (uint32_t)(dz * plane_rows + dy * g.P + dx) * RB;
-                        const uint32_t b_addr = smem_u32(b_smem + (size_t)bs * g.b_stage_bytes);
-                        const uint32_t boff = g.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+                        const uint32_t a_tap = a_lo + dz * cz + dy * cy + dx * U;
+                        const uint32_t b_tap = b_lo + (tap % G) * b_tap_units;
 #pragma unroll
                         for (int k = 0; k < KSTEPS; ++k) {
-                            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, RB, boff);
-                            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, RB, 0);
-                            umma_f16(tmem_d, adesc, bdesc, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+                            const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
+                            const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
+                            umma_f16(tmem_d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
                         }
-                        umma_commit(&b_empty[bs]);
+                        if (tap % G == G - 1) {
+                            umma_commit(&b_empty[bs]);
+                            ++itb;
+                        }
                     }
                     umma_commit(&a_empty[s]);
                 }
