@@ -18,7 +18,7 @@ LIB = os.path.join(PKG, 'libiterseg_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'),
-              '-I', CSRC]
+              '-I', CSRC] + os.environ.get('ISG_NVCC_EXTRA', '').split()
 
 
 def _newer(target, deps):

@@ -52,12 +52,16 @@ __global__ void seed_key_kernel(const int64_t *__restrict__ seeds, int64_t n,
 }
 
 // Single CTA: split the sorted seed list into components, give single-seed
-// components their fill label, multi-seed components a heap arena slice.
+// components their fill label, multi-seed components their index (MULTI_FLAG | c), a
+// size class, a slice of the compact arena (classes S/M/L) or of the global heap arena
+// (class XL), and a sort key that orders the work list largest-first.
+// scalars: [0] n_comp [1] n_multi [2,3] XL cursor/end [4,5] G [6,7] L [8,9] M [10,11] S [12] compact nodes
 __global__ void __launch_bounds__(1024)
 comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
                   const uint32_t *__restrict__ comp_size, uint32_t *__restrict__ comp_label,
                   uint32_t *__restrict__ comp_start, uint64_t *__restrict__ arena_off,
-                  uint32_t *__restrict__ n_comp_out, uint32_t *__restrict__ n_multi_out) {
+                  uint32_t *__restrict__ cbase, uint32_t *__restrict__ scalars,
+                  uint32_t *__restrict__ order_keys, uint32_t *__restrict__ order_vals) {
     typedef cub::BlockScan<uint32_t, 1024> Scan32;
     typedef cub::BlockScan<uint64_t, 1024> Scan64;
     __shared__ union {
@@ -66,9 +70,10 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
     } tmp;
     __shared__ uint32_t carry32;
     __shared__ uint64_t carry64;
-    __shared__ uint32_t multi;
+    __shared__ uint32_t cls[5];            // XL, G, L, M, S counts
     const uint32_t t = threadIdx.x;
-    if (t == 0) { carry32 = 0; carry64 = 0; multi = 0; }
+    if (t == 0) { carry32 = 0; carry64 = 0; }
+    if (t < 5) cls[t] = 0;
     __syncthreads();
     // pass 1: component heads
     for (uint32_t base = 0; base < n; base += 1024) {
@@ -97,13 +102,16 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
             if (keys[mid] == ~0ull) hi = mid; else lo = mid + 1;
         }
         comp_start[n_comp] = lo;
-        *n_comp_out = n_comp;
+        scalars[0] = n_comp;
+        carry32 = 0;                       // reused: running compact-arena offset
     }
     __syncthreads();
-    // pass 2: fill labels and arena offsets
+    // pass 2: fill labels, size classes, arena offsets
     for (uint32_t base = 0; base < n_comp; base += 1024) {
         uint32_t c = base + t;
-        uint64_t need = 0;
+        uint64_t need = 0;                 // heap entries a multi-seed component can hold
+        uint64_t arena = 0;                // global heap-arena entries (class XL only)
+        uint32_t nodes = 0;                // compact-arena nodes
         if (c < n_comp) {
             uint32_t s0 = comp_start[c], s1 = comp_start[c + 1];
             uint32_t root = (uint32_t)(keys[s0] >> 32);
@@ -111,34 +119,45 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
             if (cnt == 1) {
                 comp_label[root] = vals[s0];
             } else {
-                comp_label[root] = LABEL_MULTI;
+                comp_label[root] = MULTI_FLAG | c;
                 need = (uint64_t)comp_size[root] + cnt;
-                atomicAdd(&multi, 1u);
+                int k = need > FLOOD_CAP_G ? 0 : (need > FLOOD_CAP_L ? 1 : (need > FLOOD_CAP_M ? 2 : (need > FLOOD_CAP_S ? 3 : 4)));
+                atomicAdd(&cls[k], 1u);
+                nodes = comp_size[root];
+                if (k == 0) arena = need;
             }
         }
-        uint64_t pos, total;
-        Scan64(tmp.s64).ExclusiveSum(need, pos, total);
-        if (c < n_comp) arena_off[c] = carry64 + pos;
+        uint64_t pos64, total64;
+        Scan64(tmp.s64).ExclusiveSum(arena, pos64, total64);
         __syncthreads();
-        if (t == 0) carry64 += total;
+        uint32_t pos32, total32;
+        Scan32(tmp.s32).ExclusiveSum(nodes, pos32, total32);
+        if (c < n_comp) {
+            arena_off[c] = carry64 + pos64;
+            cbase[c] = carry32 + pos32;
+            // work list: big multi-seed components first (the largest one is the critical path)
+            order_keys[c] = need ? 0xFFFFFFFFu - (uint32_t)(need > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : need) : 0xFFFFFFFFu;
+            order_vals[c] = c;
+        }
+        __syncthreads();
+        if (t == 0) { carry64 += total64; carry32 += total32; }
         __syncthreads();
     }
     if (t == 0) {
         arena_off[n_comp] = carry64;
-        *n_multi_out = multi;
+        cbase[n_comp] = carry32;
+        uint32_t acc = 0;
+        for (int k = 0; k < 5; ++k) {          // work-list segments in sort order: XL, G, L, M, S
+            scalars[2 + 2 * k] = acc;
+            acc += cls[k];
+            scalars[3 + 2 * k] = acc;
+        }
+        scalars[1] = acc;
+        scalars[12] = carry32;
     }
-}
-
-// Single-seed components: every claimable voxel takes the seed's label.
-__global__ void __launch_bounds__(256)
-fill_single_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ comp_label,
-                   const uint8_t *__restrict__ mask, uint32_t *__restrict__ labels, uint64_t n) {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
-        uint32_t r = parent[v];
-        if (r == CCL_NONE || !mask[v]) continue;
-        uint32_t cl = comp_label[r];
-        if (cl != 0 && cl != LABEL_MULTI && labels[v] == 0) labels[v] = cl;
+    for (uint32_t c = n_comp + t; c < n; c += 1024) {      // padding up to the host-side count
+        order_keys[c] = 0xFFFFFFFFu;
+        order_vals[c] = c;
     }
 }
 
@@ -166,17 +185,56 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
     b->vals_b = cv.take<uint32_t>(max_seeds);
     b->comp_start = cv.take<uint32_t>(max_seeds + 1);
     b->arena_off = cv.take<uint64_t>(max_seeds + 1);
+    b->order_keys_a = cv.take<uint32_t>(max_seeds);
+    b->order_keys_b = cv.take<uint32_t>(max_seeds);
+    b->order_a = cv.take<uint32_t>(max_seeds);
+    b->order_b = cv.take<uint32_t>(max_seeds);
+    b->cbase = cv.take<uint32_t>(max_seeds + 1);
+    b->ccursor = cv.take<uint32_t>(max_seeds);
+    b->max_seeds = max_seeds;
     b->scalars = cv.take<uint32_t>(64);
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
                                     (uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_seeds);
     b->cub_bytes = cub_bytes + 256;
     b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
-    // heap arena: every domain voxel enters a heap at most once, plus the seeds
+    // heap arena (class XL): every domain voxel enters a heap at most once, plus the seeds
     b->arena_cap = npix + (uint64_t)max_seeds;
     b->arena_keys = cv.take<uint64_t>(b->arena_cap);
     b->arena_idx = cv.take<uint32_t>(b->arena_cap);
+    // compact component graphs (classes S/M/L): at most one node per voxel
+    b->lidmap = cv.take<uint32_t>(npix);
+    b->vox = cv.take<uint32_t>(npix);
+    b->nbr = cv.take<uint32_t>(npix * 6);
+    b->key = cv.take<uint32_t>(npix * 3);
+    b->nlab = cv.take<uint32_t>(npix);
+    b->rec = cv.take<uint32_t>(npix * 12);
     return cv.off;
+}
+
+// side streams so that the four size classes of the ordered flood run concurrently
+static constexpr int FLOOD_SIDE_STREAMS = 4;
+struct FloodStreams {
+    cudaStream_t s[FLOOD_SIDE_STREAMS];
+    cudaEvent_t fork, join[FLOOD_SIDE_STREAMS];
+    bool ok;
+};
+static FloodStreams *flood_streams() {
+    static thread_local FloodStreams fs[16];
+    static thread_local bool init[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) dev = 0;
+    if (!init[dev]) {
+        fs[dev].ok = true;
+        for (int i = 0; i < FLOOD_SIDE_STREAMS; ++i) {
+            fs[dev].ok &= cudaStreamCreateWithFlags(&fs[dev].s[i], cudaStreamNonBlocking) == cudaSuccess;
+            fs[dev].ok &= cudaEventCreateWithFlags(&fs[dev].join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        fs[dev].ok &= cudaEventCreateWithFlags(&fs[dev].fork, cudaEventDisableTiming) == cudaSuccess;
+        init[dev] = true;
+    }
+    return &fs[dev];
 }
 
 int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uint8_t *mask,
@@ -184,9 +242,11 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
                     const int64_t *seeds, int64_t n_seeds, const uint32_t *n_seeds_dev,
                     uint32_t *labels, cudaStream_t st) {
     const uint64_t npix = (uint64_t)geom.zp * geom.yp * geom.xp;
-    uint32_t *n_comp = b.scalars + 0, *n_multi = b.scalars + 1, *counter = b.scalars + 2;
     ISG_CUDA(cudaMemsetAsync(b.scalars, 0, 64 * sizeof(uint32_t), st));
     if (n_seeds <= 0) return ISG_OK;
+    ISG_REQUIRE(n_seeds <= b.max_seeds, ISG_ERR_WORKSPACE, "flood stage: %lld seeds exceed the workspace (%lld)",
+                (long long)n_seeds, (long long)b.max_seeds);
+    ISG_CUDA(cudaMemsetAsync(b.ccursor, 0, (size_t)n_seeds * sizeof(uint32_t), st));
     int blocks = (int)((n_seeds + 255) / 256);
     seed_key_kernel<<<blocks, 256, 0, st>>>(seeds, n_seeds, n_seeds_dev, parent, npix, b.keys_a,
                                             b.vals_a);
@@ -196,25 +256,86 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
                                              b.vals_b, (int)n_seeds, 0, 64, st));
     count_launch(4);
     comp_group_kernel<<<1, 1024, 0, st>>>(b.keys_b, b.vals_b, (uint32_t)n_seeds, comp_size,
-                                          comp_label, b.comp_start, b.arena_off, n_comp, n_multi);
+                                          comp_label, b.comp_start, b.arena_off, b.cbase, b.scalars,
+                                          b.order_keys_a, b.order_a);
     ISG_LAUNCHED();
+    {
+        size_t cb = b.cub_bytes;      // sized for 64-bit keys + 32-bit values: enough for 32/32
+        ISG_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, cb, b.order_keys_a, b.order_keys_b,
+                                                 b.order_a, b.order_b, (int)n_seeds, 0, 32, st));
+        count_launch(3);
+    }
     const int sms = num_sms();
-    fill_single_kernel<<<sms * 8, 256, 0, st>>>(parent, comp_label, mask, labels, npix);
+    fill_assign_kernel<<<sms * 8, 256, 0, st>>>(parent, comp_label, mask, labels, b.cbase, b.ccursor,
+                                                b.lidmap, b.vox, npix);
     ISG_LAUNCHED();
+    compact_graph_kernel<<<sms * 8, 256, 0, st>>>(geom, parent, b.lidmap, b.vox, b.scalars + 12, b.nbr,
+                                                  b.key, b.nlab, b.rec);
+    ISG_LAUNCHED();
+
     FloodWork w;
     w.seed_keys = b.keys_b;
     w.seed_labels = b.vals_b;
     w.comp_start = b.comp_start;
     w.arena_off = b.arena_off;
-    w.n_comp = n_comp;
+    w.order = b.order_b;
     w.arena_keys = b.arena_keys;
     w.arena_idx = b.arena_idx;
-    w.counter = counter;
-    const size_t smem = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
-    int64_t grid = n_seeds / 2 + 1;                     // at most n_seeds/2 multi-seed components
-    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    flood_components_kernel<<<(int)grid, 32, smem, st>>>(geom, w, mask, labels);
+    CompactGraph cg;
+    cg.cbase = b.cbase;
+    cg.vox = b.vox;
+    cg.nbr = b.nbr;
+    cg.key = b.key;
+    cg.lab = b.nlab;
+    cg.rec = b.rec;
+    cg.lidmap = b.lidmap;
+
+    const size_t smem_xl = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
+    const size_t smem_g = (size_t)FLOOD_CAP_G * 8 + FLOOD_CAP_G / 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ISG_CUDA(cudaFuncSetAttribute(flood_graph_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_xl));
+        ISG_CUDA(cudaFuncSetAttribute(flood_pq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_g));
+        ISG_CUDA(cudaFuncSetAttribute(flood_pq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(FLOOD_CAP_L * FLOOD_NODE_BYTES)));
+        attr_set = true;
+    }
+    FloodStreams *fs = flood_streams();
+    ISG_REQUIRE(fs->ok, ISG_ERR_CUDA, "flood stage: could not create side streams");
+    // upper bounds on the per-class work (the exact counts live on the device)
+    const int64_t max_multi = n_seeds / 2 + 1;
+    auto grid_for = [&](int64_t per_sm) {
+        int64_t gsz = (int64_t)sms * per_sm;
+        return (int)(gsz < max_multi ? gsz : max_multi);
+    };
+    ISG_CUDA(cudaEventRecord(fs->fork, st));
+    for (int i = 0; i < FLOOD_SIDE_STREAMS; ++i) ISG_CUDA(cudaStreamWaitEvent(fs->s[i], fs->fork, 0));
+    // the biggest classes first: G on the caller's stream, XL / L / M / S beside it
+    w.work_end = b.scalars + 5;
+    flood_pq_kernel<false><<<grid_for(1), 32, smem_g, st>>>(w, cg, FLOOD_CAP_G, b.scalars + 4, labels);
     ISG_LAUNCHED();
+    w.work_end = b.scalars + 3;
+    flood_graph_kernel<false><<<grid_for(1), 32, smem_xl, fs->s[0]>>>(w, cg, (uint32_t)FLOOD_SMEM_ENTRIES,
+                                                                       b.scalars + 2, labels);
+    ISG_LAUNCHED();
+    w.work_end = b.scalars + 7;
+    flood_pq_kernel<true><<<grid_for(1), 32, FLOOD_CAP_L * FLOOD_NODE_BYTES, fs->s[1]>>>(
+        w, cg, FLOOD_CAP_L, b.scalars + 6, labels);
+    ISG_LAUNCHED();
+    w.work_end = b.scalars + 9;
+    flood_pq_kernel<true><<<grid_for(4), 32, FLOOD_CAP_M * FLOOD_NODE_BYTES, fs->s[2]>>>(
+        w, cg, FLOOD_CAP_M, b.scalars + 8, labels);
+    ISG_LAUNCHED();
+    w.work_end = b.scalars + 11;
+    flood_pq_kernel<true><<<grid_for(16), 32, FLOOD_CAP_S * FLOOD_NODE_BYTES, fs->s[3]>>>(
+        w, cg, FLOOD_CAP_S, b.scalars + 10, labels);
+    ISG_LAUNCHED();
+    for (int i = 0; i < FLOOD_SIDE_STREAMS; ++i) {
+        ISG_CUDA(cudaEventRecord(fs->join[i], fs->s[i]));
+        ISG_CUDA(cudaStreamWaitEvent(st, fs->join[i], 0));
+    }
     return ISG_OK;
 }
 
@@ -287,3 +408,15 @@ extern "C" int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, in
     return flood_stage_run(b, g, mask, parent, comp_size, comp_label, seeds, n_seeds, nullptr, labels,
                            st);
 }
+
+#ifdef FLOOD_PROF
+extern "C" int isg_debug_flood_prof(unsigned long long *out16, int reset) {
+    ISG_CUDA(cudaDeviceSynchronize());
+    ISG_CUDA(cudaMemcpyFromSymbol(out16, isg::g_flood_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        ISG_CUDA(cudaMemcpyToSymbol(isg::g_flood_prof, z, sizeof(z)));
+    }
+    return ISG_OK;
+}
+#endif

@@ -6,7 +6,6 @@
 namespace isg {
 
 static constexpr uint32_t CCL_NONE = 0xFFFFFFFFu;
-static constexpr uint32_t LABEL_MULTI = 0xFFFFFFFFu;
 
 struct FloodGeom {
     const float *aff;          // 3 planes
@@ -23,12 +22,16 @@ struct FloodStageBuffers {
     uint32_t *vals_a, *vals_b;
     uint32_t *comp_start;
     uint64_t *arena_off;
-    uint32_t *scalars;          // [0]=n_comp [1]=n_multi [2]=work cursor
+    uint32_t *order_keys_a, *order_keys_b, *order_a, *order_b;   // components sorted by size
+    uint32_t *cbase, *ccursor;                                   // compact arena slices per component
+    int64_t max_seeds;
+    uint32_t *scalars;          // see comp_group_kernel
     unsigned char *cub_tmp;
     size_t cub_bytes;
     uint64_t *arena_keys;
     uint32_t *arena_idx;
     uint64_t arena_cap;
+    uint32_t *lidmap, *vox, *key, *nbr, *nlab, *rec;                  // compact component graphs
 };
 
 // 6-connected components of the non-zero voxels of `dom` (padded volume):

@@ -134,7 +134,8 @@ for t in mine:
     assert out[t][0] == 0 and out[t][1] == off[t] + 1 and out[t][-1] == off[t] + counts[t]
 dist.barrier()
 dist.destroy_process_group()
-print('rank', rank, 'ok')
+sys.stdout.write('rank ' + str(rank) + ' ok\n')
+sys.stdout.flush()
 '''
 
 
