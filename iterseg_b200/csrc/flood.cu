@@ -53,27 +53,31 @@ __global__ void seed_key_kernel(const int64_t *__restrict__ seeds, int64_t n,
 
 // Single CTA: split the sorted seed list into components, give single-seed
 // components their fill label, multi-seed components their index (MULTI_FLAG | c), a
-// size class, a slice of the compact arena (classes S/M/L) or of the global heap arena
-// (class XL), and a sort key that orders the work list largest-first.
-// scalars: [0] n_comp [1] n_multi [2,3] XL cursor/end [4,5] G [6,7] L [8,9] M [10,11] S [12] compact nodes
+// size class (XL = heap kernel; L / M / S = bucket-queue kernel with 227 / 54 / 13.5 KB of
+// shared memory), slices of the compact node arena and of the edge arena (bucket-queue
+// classes) or of the global heap arena (class XL), and a sort key that orders the work
+// list class by class, largest first.
+// scalars: [0] n_comp [1] n_multi [2,3] XL cursor/end [4,5] L [6,7] M [8,9] S
+//          [12] compact nodes [13] edge-arena entries
 __global__ void __launch_bounds__(1024)
 comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
                   const uint32_t *__restrict__ comp_size, uint32_t *__restrict__ comp_label,
                   uint32_t *__restrict__ comp_start, uint64_t *__restrict__ arena_off,
-                  uint32_t *__restrict__ cbase, uint32_t *__restrict__ scalars,
-                  uint32_t *__restrict__ order_keys, uint32_t *__restrict__ order_vals) {
+                  uint32_t *__restrict__ cbase, uint32_t *__restrict__ ebase,
+                  uint32_t *__restrict__ scalars, uint32_t *__restrict__ order_keys,
+                  uint32_t *__restrict__ order_vals) {
     typedef cub::BlockScan<uint32_t, 1024> Scan32;
     typedef cub::BlockScan<uint64_t, 1024> Scan64;
     __shared__ union {
         typename Scan32::TempStorage s32;
         typename Scan64::TempStorage s64;
     } tmp;
-    __shared__ uint32_t carry32;
+    __shared__ uint32_t carry32, carry_e;
     __shared__ uint64_t carry64;
-    __shared__ uint32_t cls[5];            // XL, G, L, M, S counts
+    __shared__ uint32_t cls[4];            // XL, L, M, S counts
     const uint32_t t = threadIdx.x;
-    if (t == 0) { carry32 = 0; carry64 = 0; }
-    if (t < 5) cls[t] = 0;
+    if (t == 0) { carry32 = 0; carry64 = 0; carry_e = 0; }
+    if (t < 4) cls[t] = 0;
     __syncthreads();
     // pass 1: component heads
     for (uint32_t base = 0; base < n; base += 1024) {
@@ -109,9 +113,10 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
     // pass 2: fill labels, size classes, arena offsets
     for (uint32_t base = 0; base < n_comp; base += 1024) {
         uint32_t c = base + t;
-        uint64_t need = 0;                 // heap entries a multi-seed component can hold
         uint64_t arena = 0;                // global heap-arena entries (class XL only)
         uint32_t nodes = 0;                // compact-arena nodes
+        uint32_t edges = 0;                // edge-arena entries (bucket-queue classes)
+        uint32_t okey = 0xFFFFFFFFu;
         if (c < n_comp) {
             uint32_t s0 = comp_start[c], s1 = comp_start[c + 1];
             uint32_t root = (uint32_t)(keys[s0] >> 32);
@@ -120,11 +125,21 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
                 comp_label[root] = vals[s0];
             } else {
                 comp_label[root] = MULTI_FLAG | c;
-                need = (uint64_t)comp_size[root] + cnt;
-                int k = need > FLOOD_CAP_G ? 0 : (need > FLOOD_CAP_L ? 1 : (need > FLOOD_CAP_M ? 2 : (need > FLOOD_CAP_S ? 3 : 4)));
-                atomicAdd(&cls[k], 1u);
                 nodes = comp_size[root];
-                if (k == 0) arena = need;
+                const uint64_t need = (uint64_t)nodes + cnt;       // heap entries it can hold
+                const uint64_t P = 3ull * nodes + cnt;             // bucket-queue positions
+                const uint32_t bytes = P <= BQ_MAX_POS ? bq_smem_bytes(nodes, cnt) : 0xFFFFFFFFu;
+                int k;
+                if (bytes > BQ_SMEM_L) {
+                    k = 0;
+                    arena = need;
+                    okey = 0x7FFFFFFFu - (uint32_t)(need > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : need);
+                } else {
+                    k = bytes > BQ_SMEM_M ? 1 : (bytes > BQ_SMEM_S ? 2 : 3);
+                    edges = (uint32_t)P;
+                    okey = 0x80000000u + (BQ_SMEM_L - bytes);
+                }
+                atomicAdd(&cls[k], 1u);
             }
         }
         uint64_t pos64, total64;
@@ -132,32 +147,39 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
         __syncthreads();
         uint32_t pos32, total32;
         Scan32(tmp.s32).ExclusiveSum(nodes, pos32, total32);
+        __syncthreads();
+        uint32_t pos_e, total_e;
+        Scan32(tmp.s32).ExclusiveSum(edges, pos_e, total_e);
         if (c < n_comp) {
             arena_off[c] = carry64 + pos64;
             cbase[c] = carry32 + pos32;
-            // work list: big multi-seed components first (the largest one is the critical path)
-            order_keys[c] = need ? 0xFFFFFFFFu - (uint32_t)(need > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : need) : 0xFFFFFFFFu;
+            ebase[c] = carry_e + pos_e;
+            order_keys[c] = okey;
             order_vals[c] = c;
         }
         __syncthreads();
-        if (t == 0) { carry64 += total64; carry32 += total32; }
+        if (t == 0) { carry64 += total64; carry32 += total32; carry_e += total_e; }
         __syncthreads();
     }
     if (t == 0) {
         arena_off[n_comp] = carry64;
         cbase[n_comp] = carry32;
         uint32_t acc = 0;
-        for (int k = 0; k < 5; ++k) {          // work-list segments in sort order: XL, G, L, M, S
+        for (int k = 0; k < 4; ++k) {          // work-list segments in sort order: XL, L, M, S
             scalars[2 + 2 * k] = acc;
             acc += cls[k];
             scalars[3 + 2 * k] = acc;
         }
         scalars[1] = acc;
         scalars[12] = carry32;
+        scalars[13] = carry_e;
     }
-    for (uint32_t c = n_comp + t; c < n; c += 1024) {      // padding up to the host-side count
-        order_keys[c] = 0xFFFFFFFFu;
-        order_vals[c] = c;
+    for (uint32_t c = n_comp + t; c <= n; c += 1024) {     // padding up to the host-side count
+        if (c < n) {
+            order_keys[c] = 0xFFFFFFFFu;
+            order_vals[c] = c;
+        }
+        ebase[c] = carry_e;                                 // empty segments (carry_e is final)
     }
 }
 
@@ -202,18 +224,36 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
     b->arena_cap = npix + (uint64_t)max_seeds;
     b->arena_keys = cv.take<uint64_t>(b->arena_cap);
     b->arena_idx = cv.take<uint32_t>(b->arena_cap);
-    // compact component graphs (classes S/M/L): at most one node per voxel
+    // compact component graphs: at most one node per voxel
     b->lidmap = cv.take<uint32_t>(npix);
     b->vox = cv.take<uint32_t>(npix);
     b->nbr = cv.take<uint32_t>(npix * 6);
     b->key = cv.take<uint32_t>(npix * 3);
     b->nlab = cv.take<uint32_t>(npix);
-    b->rec = cv.take<uint32_t>(npix * 12);
+    b->rec = cv.take<uint4>(npix * 2);
+    // edge arena of the bucket-queue classes: 3 stored edges per node + one entry per seed
+    b->ebase = cv.take<uint32_t>(max_seeds + 1);
+    b->edge_cap = npix * 3 + (uint64_t)max_seeds;
+    b->ekeys_a = cv.take<uint32_t>(b->edge_cap);
+    b->ekeys_b = cv.take<uint32_t>(b->edge_cap);
+    b->evals_a = cv.take<uint32_t>(b->edge_cap);
+    b->evals_b = cv.take<uint32_t>(b->edge_cap);
+    b->seedpos = cv.take<uint32_t>(max_seeds);
+    b->complab = cv.take<uint32_t>(max_seeds);
+    {
+        cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+        size_t seg_bytes = 0;
+        const int items = (int)(b->edge_cap > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : b->edge_cap);
+        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, seg_bytes, dk, dv, items, (int)max_seeds,
+                                                 (const uint32_t *)nullptr, (const uint32_t *)nullptr);
+        b->seg_bytes = seg_bytes + 256;
+        b->seg_tmp = cv.take<unsigned char>(b->seg_bytes);
+    }
     return cv.off;
 }
 
-// side streams so that the four size classes of the ordered flood run concurrently
-static constexpr int FLOOD_SIDE_STREAMS = 4;
+// side streams so that the size classes of the ordered flood run concurrently
+static constexpr int FLOOD_SIDE_STREAMS = 3;
 struct FloodStreams {
     cudaStream_t s[FLOOD_SIDE_STREAMS];
     cudaEvent_t fork, join[FLOOD_SIDE_STREAMS];
@@ -256,8 +296,8 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
                                              b.vals_b, (int)n_seeds, 0, 64, st));
     count_launch(4);
     comp_group_kernel<<<1, 1024, 0, st>>>(b.keys_b, b.vals_b, (uint32_t)n_seeds, comp_size,
-                                          comp_label, b.comp_start, b.arena_off, b.cbase, b.scalars,
-                                          b.order_keys_a, b.order_a);
+                                          comp_label, b.comp_start, b.arena_off, b.cbase, b.ebase,
+                                          b.scalars, b.order_keys_a, b.order_a);
     ISG_LAUNCHED();
     {
         size_t cb = b.cub_bytes;      // sized for 64-bit keys + 32-bit values: enough for 32/32
@@ -269,13 +309,32 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     fill_assign_kernel<<<sms * 8, 256, 0, st>>>(parent, comp_label, mask, labels, b.cbase, b.ccursor,
                                                 b.lidmap, b.vox, npix);
     ISG_LAUNCHED();
-    compact_graph_kernel<<<sms * 8, 256, 0, st>>>(geom, parent, b.lidmap, b.vox, b.scalars + 12, b.nbr,
-                                                  b.key, b.nlab, b.rec);
+    seed_edge_kernel<<<blocks, 256, 0, st>>>(b.keys_b, (uint32_t)n_seeds, comp_label, b.comp_start,
+                                             b.ebase, b.ekeys_a, b.evals_a);
     ISG_LAUNCHED();
+    compact_graph_kernel<<<sms * 8, 256, 0, st>>>(geom, parent, comp_label, b.comp_start, b.cbase, b.ebase,
+                                                  b.lidmap, b.vox, b.scalars + 12, b.nbr, b.key, b.nlab,
+                                                  b.rec, b.ekeys_a, b.evals_a);
+    ISG_LAUNCHED();
+    // rank the edge values of every bucket-queue component (one segment each; stable)
+    cub::DoubleBuffer<uint32_t> dk(b.ekeys_a, b.ekeys_b), dv(b.evals_a, b.evals_b);
+    {
+        size_t sb = b.seg_bytes;
+        const int items = (int)(b.edge_cap > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : b.edge_cap);
+        ISG_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(b.seg_tmp, sb, dk, dv, items, (int)n_seeds,
+                                                          b.ebase, b.ebase + 1, 0, 32, st));
+        count_launch(4);
+    }
+    {
+        const int64_t g = n_seeds < (int64_t)sms * 8 ? n_seeds : (int64_t)sms * 8;
+        edge_group_kernel<<<(int)g, 256, 0, st>>>(b.scalars, b.ebase, b.cbase, b.comp_start, dk.Current(),
+                                                  dv.Current(), reinterpret_cast<uint16_t *>(b.rec),
+                                                  b.seedpos);
+        ISG_LAUNCHED();
+    }
 
     FloodWork w;
     w.seed_keys = b.keys_b;
-    w.seed_labels = b.vals_b;
     w.comp_start = b.comp_start;
     w.arena_off = b.arena_off;
     w.order = b.order_b;
@@ -287,19 +346,23 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     cg.nbr = b.nbr;
     cg.key = b.key;
     cg.lab = b.nlab;
-    cg.rec = b.rec;
     cg.lidmap = b.lidmap;
+    BqGraph bq;
+    bq.cbase = b.cbase;
+    bq.ebase = b.ebase;
+    bq.vox = b.vox;
+    bq.lidmap = b.lidmap;
+    bq.rec = b.rec;
+    bq.seedpos = b.seedpos;
+    bq.complab = b.complab;
 
     const size_t smem_xl = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
-    const size_t smem_g = (size_t)FLOOD_CAP_G * 8 + FLOOD_CAP_G / 8;
     static bool attr_set = false;
     if (!attr_set) {
-        ISG_CUDA(cudaFuncSetAttribute(flood_graph_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ISG_CUDA(cudaFuncSetAttribute(flood_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem_xl));
-        ISG_CUDA(cudaFuncSetAttribute(flood_pq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_g));
-        ISG_CUDA(cudaFuncSetAttribute(flood_pq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(FLOOD_CAP_L * FLOOD_NODE_BYTES)));
+        ISG_CUDA(cudaFuncSetAttribute(flood_bq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BQ_SMEM_L));
         attr_set = true;
     }
     FloodStreams *fs = flood_streams();
@@ -312,25 +375,19 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     };
     ISG_CUDA(cudaEventRecord(fs->fork, st));
     for (int i = 0; i < FLOOD_SIDE_STREAMS; ++i) ISG_CUDA(cudaStreamWaitEvent(fs->s[i], fs->fork, 0));
-    // the biggest classes first: G on the caller's stream, XL / L / M / S beside it
+    // the biggest classes first: L on the caller's stream, XL / M / S beside it
     w.work_end = b.scalars + 5;
-    flood_pq_kernel<false><<<grid_for(1), 32, smem_g, st>>>(w, cg, FLOOD_CAP_G, b.scalars + 4, labels);
+    flood_bq_kernel<<<grid_for(1), 32, BQ_SMEM_L, st>>>(w, bq, b.scalars + 4, labels);
     ISG_LAUNCHED();
     w.work_end = b.scalars + 3;
-    flood_graph_kernel<false><<<grid_for(1), 32, smem_xl, fs->s[0]>>>(w, cg, (uint32_t)FLOOD_SMEM_ENTRIES,
-                                                                       b.scalars + 2, labels);
+    flood_heap_kernel<<<grid_for(1), 32, smem_xl, fs->s[0]>>>(w, cg, (uint32_t)FLOOD_SMEM_ENTRIES,
+                                                               b.scalars + 2, labels);
     ISG_LAUNCHED();
     w.work_end = b.scalars + 7;
-    flood_pq_kernel<true><<<grid_for(1), 32, FLOOD_CAP_L * FLOOD_NODE_BYTES, fs->s[1]>>>(
-        w, cg, FLOOD_CAP_L, b.scalars + 6, labels);
+    flood_bq_kernel<<<grid_for(4), 32, BQ_SMEM_M, fs->s[1]>>>(w, bq, b.scalars + 6, labels);
     ISG_LAUNCHED();
     w.work_end = b.scalars + 9;
-    flood_pq_kernel<true><<<grid_for(4), 32, FLOOD_CAP_M * FLOOD_NODE_BYTES, fs->s[2]>>>(
-        w, cg, FLOOD_CAP_M, b.scalars + 8, labels);
-    ISG_LAUNCHED();
-    w.work_end = b.scalars + 11;
-    flood_pq_kernel<true><<<grid_for(16), 32, FLOOD_CAP_S * FLOOD_NODE_BYTES, fs->s[3]>>>(
-        w, cg, FLOOD_CAP_S, b.scalars + 10, labels);
+    flood_bq_kernel<<<grid_for(16), 32, BQ_SMEM_S, fs->s[2]>>>(w, bq, b.scalars + 8, labels);
     ISG_LAUNCHED();
     for (int i = 0; i < FLOOD_SIDE_STREAMS; ++i) {
         ISG_CUDA(cudaEventRecord(fs->join[i], fs->s[i]));

@@ -9,13 +9,13 @@
 //     component is flooded on its own with a local age counter;
 //   * a component holding exactly one seed is filled with that seed's label
 //     (a plain parallel pass); a component without seeds stays 0;
-//   * only components with >= 2 seeds run the ordered flood: one warp per
-//     component, a 32-ary min-heap of 64-bit keys (order-preserving float bits
-//     << 32 | age) in shared memory (global arena for big components), the six
-//     neighbour tests of a popped voxel done by six lanes at once.
+//   * only components with >= 2 seeds run the ordered flood, each on its own compacted
+//     graph: flood_bq_kernel (an exact O(1) bucket queue over the component's ranked edge
+//     values, one thread per component, queue in shared memory) and, for components too
+//     big for that, flood_heap_kernel (one warp per component, 32-ary heap).
 // Seeds carry value 0.0 / age 0 in the reference and are ordered by flat index
-// (third tuple field, watershed.py:162); here they get ages 0..k-1 in index
-// order and pushes continue from k, which preserves every comparison.
+// (third tuple field, watershed.py:162); both kernels queue them first, in index order,
+// among the entries of value 0.0, which preserves every comparison.
 #pragma once
 #include "ccl.cuh"
 #include "flood_stage.h"
@@ -24,22 +24,14 @@ namespace isg {
 
 static constexpr int FLOOD_SMEM_ENTRIES = 18816;     // class XL: heap slots [0, 18816) (12 B each, 220.5 KB)
                                                      // live in shared memory, the rest in the global arena
-
-// Size classes of the shared-memory flood (flood_compact_kernel): a component whose
-// node count + seed count fits CAP runs entirely out of shared memory
-// (36 B per node: heap u64, 3 edge keys u32, label u32, 6 neighbour ids u16).
-static constexpr uint32_t FLOOD_CAP_S = 384;         // 13.5 KB -> 16 warps-CTAs per SM
-static constexpr uint32_t FLOOD_CAP_M = 1536;        // 54 KB   -> 4 per SM
-static constexpr uint32_t FLOOD_CAP_L = 6272;        // 220.5 KB -> 1 per SM
-static constexpr uint32_t FLOOD_NODE_BYTES = 36;
 static constexpr uint32_t MULTI_FLAG = 0x80000000u;  // comp_label[root] = MULTI_FLAG | component index
 static constexpr uint32_t NO_NODE = 0xFFFFu;
+static constexpr uint32_t NO_NODE32 = 0xFFFFFFFFu;
 
 struct FloodWork {
     const uint64_t *seed_keys;     // sorted (root << 32 | padded flat index)
-    const uint32_t *seed_labels;   // label of the seed at the same sorted position
     const uint32_t *comp_start;    // n_comp + 1 offsets into the sorted arrays
-    const uint64_t *arena_off;     // per component offset into the heap arena
+    const uint64_t *arena_off;     // per component offset into the heap arena (class XL)
     const uint32_t *work_end;      // device scalar: number of work-list entries for this kernel
     const uint32_t *order;         // component indices, largest first
     uint64_t *arena_keys;
@@ -60,55 +52,35 @@ __device__ __forceinline__ float flood_key_value(const FloodGeom &g, int axis, f
     return v + 0.0f;
 }
 
-// ---------------------------------------------------------------------------
-// Ordered flood of one component per warp over its compacted graph
-// ---------------------------------------------------------------------------
 // Every multi-seed component is first compacted (fill_assign_kernel, compact_graph_kernel):
-// its voxels get dense local ids (their order is irrelevant: no comparison ever reaches the id
-// bits), and per node the six neighbour ids (NO_NODE = not claimable) and the three edge keys
-// stored at the voxel (order-preserving bits of aff / channel_max).
-//   SMEM = true  (classes S/M/L): graph, labels and heap live in shared memory; heap entries
-//                are single 64-bit words (key << 32 | age << 16 | node).  No global access on
-//                the pop -> expand -> push critical path.
-//   SMEM = false (class XL): the graph stays in global memory (L2-resident), the loads of a
-//                popped node are issued before / during the sift-down so their latency hides
-//                behind it; heap = (key << 32 | age, node) pairs, the first `cap` slots in
-//                shared memory and the rest in the global arena.
+// its voxels get dense local ids (their order is irrelevant: no comparison ever reaches the
+// id bits), and per node the six neighbour ids (NO_NODE = not claimable) and the edge keys
+// (order-preserving bits of aff / channel_max).
+
+// ---------------------------------------------------------------------------
+// flood_heap_kernel (class XL: components too big for the bucket queue below)
+// ---------------------------------------------------------------------------
+// One warp per component, a 32-ary min-heap of (key << 32 | age, node) pairs: the first
+// `cap` slots in shared memory, the rest in the global arena; pop = 2x redux.sync.min per
+// level, the six neighbour tests done by six lanes, the graph in global memory (L2) with
+// the loads of a popped node issued before / during the sift-down.
 struct CompactGraph {
     const uint32_t *cbase;         // [n_comp + 1] first node of component c (compact arena)
     const uint32_t *vox;           // [total] padded flat voxel index of every node
     const uint32_t *nbr;           // [total][6]  (NO_NODE32 = not claimable)
     const uint32_t *key;           // [total][3]
-    const uint32_t *rec;           // [total][12] {6 neighbours, 6 edge keys} (global-graph mode)
-    uint32_t *lab;                 // [total] node labels (class XL; zeroed by compact_graph_kernel)
+    uint32_t *lab;                 // [total] node labels (zeroed by compact_graph_kernel)
     const uint32_t *lidmap;        // [npix] voxel -> local id
 };
-static constexpr uint32_t NO_NODE32 = 0xFFFFFFFFu;
 
-#ifdef FLOOD_PROF
-// debug: [SMEM][0..7] = pops, sift clocks, expand clocks, push clocks, pushes, prefetch hits, levels, max heap
-__device__ unsigned long long g_flood_prof[2][8];
-#define FP_T(x) const long long x = clock64()
-#define FP_ADD(i, v) prof[i] += (unsigned long long)(v)
-#else
-#define FP_T(x)
-#define FP_ADD(i, v)
-#endif
-
-template <bool SMEM>
 __global__ void __launch_bounds__(32)
-flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, uint32_t *labels) {
+flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, uint32_t *labels) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x;
     const uint32_t work_end = *w.work_end;
-    // SMEM layout: heap u64[cap] | key u32[3 cap] | lab u32[cap] | nbr u16[6 cap]
-    // XL layout:   heap keys u64[cap] | heap nodes u32[cap]
     uint64_t *const heap = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *const skey = reinterpret_cast<uint32_t *>(smem_raw + (size_t)cap * 8);
-    uint32_t *const slab = skey + (size_t)cap * 3;
-    uint16_t *const snbr = reinterpret_cast<uint16_t *>(slab + cap);
-    uint32_t *const hnode = skey;                                    // XL only
+    uint32_t *const hnode = reinterpret_cast<uint32_t *>(smem_raw + (size_t)cap * 8);
     const int axis = lane < 3 ? (int)lane : (lane < 6 ? 5 - (int)lane : 0);   // [0,1,2,2,1,0]
 
     for (;;) {
@@ -122,23 +94,11 @@ flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor,
         const uint32_t *const gkey = cg.key + (size_t)b0 * 3;
         const uint32_t *const gnbr = cg.nbr + (size_t)b0 * 6;
         uint32_t *const glab = cg.lab + b0;
-        uint64_t *const akeys = w.arena_keys + w.arena_off[c];       // XL heap overflow
+        uint64_t *const akeys = w.arena_keys + w.arena_off[c];       // heap overflow
         uint32_t *const anode = w.arena_idx + w.arena_off[c];
         __syncwarp();                                   // previous component's smem reads are done
-        if (SMEM) {   // stage the component graph (coalesced copies)
-            for (uint32_t i = lane; i < nv * 3; i += 32) skey[i] = gkey[i];
-            for (uint32_t i = lane; i < nv * 6; i += 32) snbr[i] = (uint16_t)gnbr[i];   // NO_NODE32 -> NO_NODE
-            for (uint32_t i = lane; i < nv; i += 32) slab[i] = 0;
-            __syncwarp();
-        }
-        // heap accessors (slot -> storage)
-        auto hk_ld = [&](uint32_t i) -> uint64_t {
-            if (SMEM) return heap[i];
-            return i < cap ? heap[i] : akeys[i];
-        };
-        auto hk_st = [&](uint32_t i, uint64_t k) {
-            if (SMEM || i < cap) heap[i] = k; else akeys[i] = k;
-        };
+        auto hk_ld = [&](uint32_t i) -> uint64_t { return i < cap ? heap[i] : akeys[i]; };
+        auto hk_st = [&](uint32_t i, uint64_t k) { if (i < cap) heap[i] = k; else akeys[i] = k; };
         auto hn_ld = [&](uint32_t i) -> uint32_t { return i < cap ? hnode[i] : anode[i]; };
         auto hn_st = [&](uint32_t i, uint32_t x) { if (i < cap) hnode[i] = x; else anode[i] = x; };
 
@@ -146,50 +106,28 @@ flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor,
         for (uint32_t i = lane; i < cnt; i += 32) {
             const uint32_t v = (uint32_t)(w.seed_keys[s0 + i] & 0xFFFFFFFFu);
             const uint32_t lid = cg.lidmap[v];
-            const uint32_t l = labels[v];    // the final seed label (duplicates: largest, set upstream)
-            if (SMEM) {
-                heap[i] = zero_hi | ((uint64_t)i << 16) | lid;     // ascending array == valid heap
-                slab[lid] = l;
-            } else {
-                hk_st(i, zero_hi | i);
-                hn_st(i, lid);
-                __stcg(glab + lid, l);
-            }
+            hk_st(i, zero_hi | i);           // ascending array == valid heap
+            hn_st(i, lid);
+            __stcg(glab + lid, labels[v]);   // the final seed label (duplicates: largest, set upstream)
         }
         uint32_t n = cnt;
         uint32_t age = cnt;
-        uint32_t pref_node = NO_NODE32, pref_nb = NO_NODE32;   // XL: speculative adjacency prefetch
-#ifdef FLOOD_PROF
-        unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
+        uint32_t pref_node = NO_NODE32, pref_nb = NO_NODE32;   // speculative adjacency prefetch
         __syncwarp();
 
         while (n > 0) {
             // ---- pop the minimum -------------------------------------------------
-            FP_T(t0);
-            FP_ADD(0, 1);
-#ifdef FLOOD_PROF
-            if (n > prof[7]) prof[7] = n;
-#endif
-            uint32_t p;
-            if (SMEM) p = (uint32_t)heap[0] & 0xFFFFu; else p = hnode[0];
+            const uint32_t p = hnode[0];
             --n;
             const uint64_t lastk = hk_ld(n);
-            uint32_t lastn = 0;
-            if (!SMEM) lastn = hn_ld(n);
-            // expansion loads, part 1 (in flight during the sift-down)
-            uint32_t nb = NO_NODE32, labp;
-            if (SMEM) {
-                if (lane < 6) { const uint32_t t = snbr[p * 6u + lane]; nb = t == NO_NODE ? NO_NODE32 : t; }
-                labp = slab[p];
-            } else {
-                // the adjacency of the node that was on top after the previous sift-down was
-                // requested back then; unless a push displaced it, it has long arrived
-                if (pref_node == p) nb = pref_nb;
-                else if (lane < 6) nb = __ldg(gnbr + (size_t)p * 6u + lane);
-                labp = __ldcg(glab + p);
-            }
-            const bool pref_hit = !SMEM && pref_node == p;
+            const uint32_t lastn = hn_ld(n);
+            // expansion loads, part 1 (in flight during the sift-down): the adjacency of the
+            // node that was on top after the previous sift-down was requested back then
+            uint32_t nb = NO_NODE32;
+            const bool pref_hit = pref_node == p;
+            if (pref_hit) nb = pref_nb;
+            else if (lane < 6) nb = __ldg(gnbr + (size_t)p * 6u + lane);
+            const uint32_t labp = __ldcg(glab + p);
             uint32_t labn = 1, kord = 0;
             bool fetched = false;
             auto fetch2 = [&]() {        // expansion loads, part 2: need nb
@@ -197,12 +135,12 @@ flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor,
                     // edge key: stored at the popped voxel for the three negative directions,
                     // at the neighbour for the positive ones
                     const size_t kn = (size_t)(lane < 3 ? p : nb) * 3u + axis;
-                    if (SMEM) { labn = slab[nb]; kord = skey[kn]; }
-                    else { labn = __ldcg(glab + nb); kord = __ldg(gkey + kn); }
+                    labn = __ldcg(glab + nb);
+                    kord = __ldg(gkey + kn);
                 }
                 fetched = true;
             };
-            if (pref_hit) { fetch2(); FP_ADD(5, 1); }    // adjacency already here: start the dependent loads
+            if (pref_hit) fetch2();
             __syncwarp();                                // all lanes hold p / last before slot 0 changes
             if (n > 0) {
                 uint32_t i = 0;
@@ -221,37 +159,28 @@ flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor,
                     const uint32_t wc = c0 + win;
                     if (lane == 0) {
                         hk_st(i, mk);
-                        if (!SMEM) hn_st(i, hn_ld(wc));
+                        hn_st(i, hn_ld(wc));
                     }
                     __syncwarp();
                     i = wc;
-                    FP_ADD(6, 1);
                     if (!fetched) fetch2();
                 }
                 if (lane == 0) {
                     hk_st(i, lastk);
-                    if (!SMEM) hn_st(i, lastn);
+                    hn_st(i, lastn);
                 }
                 __syncwarp();
-                if (!SMEM) {                             // request the adjacency of the likely next pop
-                    pref_node = hnode[0];
-                    pref_nb = NO_NODE32;
-                    if (lane < 6) pref_nb = __ldg(gnbr + (size_t)pref_node * 6u + lane);
-                }
+                pref_node = hnode[0];                    // request the adjacency of the likely next pop
+                pref_nb = NO_NODE32;
+                if (lane < 6) pref_nb = __ldg(gnbr + (size_t)pref_node * 6u + lane);
             }
             if (!fetched) fetch2();
-            FP_T(t1);
             // ---- expand the popped node (watershed.py:135-154) ---------------------
             const bool claim = nb != NO_NODE32 && labn == 0;
             unsigned bits = __ballot_sync(FULL, claim);
-            FP_T(t2);
-            FP_ADD(4, __popc(bits));
-            if (claim) {                                  // labelled at push time (:149)
-                if (SMEM) slab[nb] = labp; else __stcg(glab + nb, labp);
-            }
+            if (claim) __stcg(glab + nb, labp);           // labelled at push time (:149)
             const uint32_t myage = age + __popc(bits & ((1u << lane) - 1u));
-            const uint64_t mykey = SMEM ? (((uint64_t)kord << 32) | ((uint64_t)myage << 16) | nb)
-                                        : (((uint64_t)kord << 32) | myage);
+            const uint64_t mykey = ((uint64_t)kord << 32) | myage;
             age += __popc(bits);
             __syncwarp();
             while (bits) {
@@ -266,70 +195,97 @@ flood_graph_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor,
                     if (pk <= k) break;
                     if (lane == 0) {
                         hk_st(i, pk);
-                        if (!SMEM) hn_st(i, hn_ld(par));
+                        hn_st(i, hn_ld(par));
                     }
                     i = par;
                 }
                 if (lane == 0) {
                     hk_st(i, k);
-                    if (!SMEM) hn_st(i, kn);
+                    hn_st(i, kn);
                 }
                 __syncwarp();
             }
-            FP_T(t3);
-            FP_ADD(1, t1 - t0);
-            FP_ADD(2, t2 - t1);
-            FP_ADD(3, t3 - t2);
         }
-#ifdef FLOOD_PROF
-        if (lane == 0 && nv > 5000) {
-            for (int q = 0; q < 7; ++q) atomicAdd(&g_flood_prof[SMEM ? 1 : 0][q], prof[q]);
-            atomicMax(&g_flood_prof[SMEM ? 1 : 0][7], prof[7]);
-        }
-#endif
         // ---- write the component's labels back ---------------------------------------
         __syncwarp();
-        for (uint32_t i = lane; i < nv; i += 32)
-            labels[cg.vox[b0 + i]] = SMEM ? slab[i] : __ldcg(glab + i);
+        for (uint32_t i = lane; i < nv; i += 32) labels[cg.vox[b0 + i]] = __ldcg(glab + i);
     }
 }
 
 // ---------------------------------------------------------------------------
-// flood_pq_kernel: the fast ordered flood (classes S / M / L with the graph in shared
-// memory, class G with the graph in global memory)
+// flood_bq_kernel: the fast ordered flood -- an exact bucket queue
 // ---------------------------------------------------------------------------
-// Priority queue = a 32-ary min-heap in shared memory PLUS a small pending buffer of
-// PS entries held in (warp-uniform) registers.  New keys go to the pending buffer for
-// free; a pop takes min(pending minimum, heap top).  The very common cascade "a freshly
-// pushed voxel is the next one popped" therefore never touches the heap, and a heap pop
-// re-uses the vacated root for the largest pending entry (one sift-down instead of a
-// sift-down plus a sift-up).  Keys are unique 64-bit words (value bits | age | node), so
-// any implementation of "pop the minimum" yields the reference order.
-//   GSMEM = true : per node {6 x u16 neighbour, 3 x u32 key, u32 label} staged in smem.
-//   GSMEM = false: per node one 48-byte record {6 neighbours, 6 edge keys} in global
-//                  memory, requested when the node enters the queue (pending slot
-//                  registers) or becomes the heap top, so that its latency hides behind
-//                  the queue work; claimed-bits in smem, labels in global memory.
-static constexpr int FLOOD_PS = 8;                   // pending-buffer slots
-static constexpr uint32_t FLOOD_CAP_G = 28160;       // class G: heap entries (8 B) + claimed bits: 223.4 KB
+// The reference heap orders entries by (value, age) (watershed.py:162).  Inside one
+// component the values that can ever be queued are known before the flood starts: a voxel
+// is queued with the affinity of the edge it was claimed through, so the universe is the
+// component's edge list (+ one value-0.0 pseudo edge per seed).  The edges are ranked once,
+// in parallel (segmented radix sort of the order-preserving float bits, one segment per
+// component; edge_group_kernel turns ranks into "group start" positions, a group being a
+// run of equal values).  The queue is then a set of POSITIONS:
+//   push(edge) : position = group start + tail[group]++ ;  slots[position] = node
+//   pop        : the lowest queued position
+// Equal values pop in insertion order because a group's positions are handed out in
+// ascending order: exactly the reference's age tie-break, with no age counter at all.  An
+// edge is used for at most one push (after it both end points are labelled), so a group
+// never overflows.  Seeds are the first entries of the 0.0 group in flat-index order (the
+// reference's (0.0, 0, index) tuples).
+//
+// One warp per component.  The set of queued positions is split in two:
+//   * the FRONT: at most 32 entries (position << 16 | node), one per lane, in registers;
+//     every front entry is below `bmin`;
+//   * the BACK: a two-level bitmap over positions in shared memory; every back entry is at
+//     or above `bmin`.
+// pop = redux.min over the front (one instruction); a push below bmin goes to a free front
+// lane, the others set a bit in the back.  When the front runs empty it is refilled from
+// the first 32 non-empty-or-not bitmap words at once (one word per lane) and bmin moves up.
+// The six neighbour tests of a popped node are done by six lanes.  The read-only node
+// record {6 neighbours, 6 group starts} (32 B) stays in global memory (L2); the lane that
+// receives a front entry requests it right away with cp.async into its own staging slot, so
+// that the fetch overlaps the pops in front of it (a cp.async holds no register scoreboard,
+// a plain load would serialise the whole warp behind it).
+// Queue + labels take ~14.1 B of shared memory per node -> components of up to ~16 000
+// voxels; bigger ones take the heap kernel above (class XL).
+static constexpr uint32_t BQ_SMEM_S = 13824;         // 16 components per SM
+static constexpr uint32_t BQ_SMEM_M = 55296;         // 4 per SM
+static constexpr uint32_t BQ_SMEM_L = 232448;        // 1 per SM (227 KB)
+static constexpr uint32_t BQ_SEED_FLAG = 0x80000000u;
+static constexpr uint32_t BQ_MAX_POS = 65535u;       // positions and node ids are 16-bit
+static constexpr uint32_t BQ_HEADER = 1024u + 128u;  // 32 record staging slots + refill scratch
 
-template <bool GSMEM>
+__host__ __device__ __forceinline__ uint32_t bq_smem_bytes(uint32_t nodes, uint32_t seeds) {
+    const uint32_t P = 3u * nodes + seeds;
+    const uint32_t n0 = (P + 31u) / 32u, n1 = (n0 + 31u) / 32u;
+    return BQ_HEADER + ((4u * P + 2u * nodes + 3u) & ~3u) + 4u * n0 + 4u * n1;
+}
+
+#ifdef FLOOD_PROF
+// debug: [0] pops [1] refills [2] front pushes [3] back pushes [4] evictions [6] total clocks
+__device__ unsigned long long g_flood_prof[16];
+#define FP_ADD(i, v) prof[i] += (unsigned long long)(v)
+#else
+#define FP_ADD(i, v)
+#endif
+
+struct BqGraph {
+    const uint32_t *cbase;         // [n_comp + 1] first node of component c (compact arena)
+    const uint32_t *ebase;         // [n_comp + 1] first queue position (edge arena); empty = class XL
+    const uint32_t *vox;           // [total] padded flat voxel index of every node
+    const uint32_t *lidmap;        // [npix] voxel -> local id
+    const uint4 *rec;              // [total][2] u16 x {6 neighbours, 6 group starts, 4 pad}
+    const uint32_t *seedpos;       // [n_seeds] queue position of the i-th sorted seed
+    uint32_t *complab;             // [n_seeds] final label of the i-th sorted seed
+};
+
 __global__ void __launch_bounds__(32)
-flood_pq_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, uint32_t *labels) {
+flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x;
     const uint32_t work_end = *w.work_end;
-    // GSMEM layout: heap u64[cap] | key u32[3 cap] | lab u32[cap] | nbr u16[6 cap]
-    // global-graph layout: heap u64[cap] | claimed bits u32[cap / 32]
-    uint64_t *const heap = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *const skey = reinterpret_cast<uint32_t *>(smem_raw + (size_t)cap * 8);
-    uint32_t *const slab = skey + (size_t)cap * 3;
-    uint16_t *const snbr = reinterpret_cast<uint16_t *>(slab + cap);
-    uint32_t *const sbits = skey;                                    // global-graph mode
-    const int axis = lane < 3 ? (int)lane : (lane < 6 ? 5 - (int)lane : 0);   // [0,1,2,2,1,0]
-    const uint64_t EMPTY = ~0ull;
-
+    const uint32_t EMPTY = 0xFFFFFFFFu;
+    const uint16_t *const stage16 = reinterpret_cast<const uint16_t *>(smem_raw);
+    uint32_t *const scratch = reinterpret_cast<uint32_t *>(smem_raw + 1024);
+    const uint32_t my_stage = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 32u;
     for (;;) {
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(cursor, 1u);
@@ -337,200 +293,259 @@ flood_pq_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, ui
         if (wi >= work_end) break;
         const uint32_t c = w.order[wi];
         const uint32_t s0 = w.comp_start[c], cnt = w.comp_start[c + 1] - s0;
-        const uint32_t b0 = cg.cbase[c], nv = cg.cbase[c + 1] - b0;
-        const uint32_t *const grec = cg.rec + (size_t)b0 * 12;
-        uint32_t *const glab = cg.lab + b0;
+        const uint32_t b0 = g.cbase[c], nv = g.cbase[c + 1] - b0;
+        const uint32_t P = 3u * nv + cnt;
+        const uint32_t n0 = (P + 31u) / 32u, n1 = (n0 + 31u) / 32u;
+        uint16_t *const slots = reinterpret_cast<uint16_t *>(smem_raw + BQ_HEADER);
+        uint16_t *const tail = slots + P;
+        uint16_t *const slab = tail + P;
+        uint32_t *const L0 = reinterpret_cast<uint32_t *>(smem_raw + BQ_HEADER + ((4u * P + 2u * nv + 3u) & ~3u));
+        uint32_t *const L1 = L0 + n0;
+        const uint4 *const rec = g.rec + (size_t)b0 * 2;
         __syncwarp();                                   // previous component's smem reads are done
-        if (GSMEM) {   // stage the component graph (coalesced copies)
-            const uint32_t *const gkey = cg.key + (size_t)b0 * 3;
-            const uint32_t *const gnbr = cg.nbr + (size_t)b0 * 6;
-            for (uint32_t i = lane; i < nv * 3; i += 32) skey[i] = gkey[i];
-            for (uint32_t i = lane; i < nv * 6; i += 32) snbr[i] = (uint16_t)gnbr[i];   // NO_NODE32 -> NO_NODE
-            for (uint32_t i = lane; i < nv; i += 32) slab[i] = 0;
-        } else {
-            for (uint32_t i = lane; i < (nv + 31) / 32; i += 32) sbits[i] = 0;
-        }
+        for (uint32_t i = lane; i < P; i += 32) tail[i] = 0;
+        for (uint32_t i = lane; i < nv; i += 32) slab[i] = 0;
+        for (uint32_t i = lane; i < n0 + n1; i += 32) L0[i] = 0;
         __syncwarp();
-        const uint64_t zero_hi = (uint64_t)f32_ord(0.0f) << 32;
         for (uint32_t i = lane; i < cnt; i += 32) {
             const uint32_t v = (uint32_t)(w.seed_keys[s0 + i] & 0xFFFFFFFFu);
-            const uint32_t lid = cg.lidmap[v];
-            const uint32_t l = labels[v];    // the final seed label (duplicates: largest, set upstream)
-            heap[i] = zero_hi | ((uint64_t)i << 16) | lid;         // ascending array == valid heap
-            if (GSMEM) slab[lid] = l;
-            else { atomicOr(sbits + (lid >> 5), 1u << (lid & 31)); __stcg(glab + lid, l); }
+            const uint32_t lid = g.lidmap[v];
+            const uint32_t pos = g.seedpos[s0 + i];
+            g.complab[s0 + i] = labels[v];   // the final seed label (duplicates: largest, set upstream)
+            slots[pos] = (uint16_t)lid;
+            slab[lid] = (uint16_t)(i + 1);   // duplicated seeds carry the same final label
+            atomicOr(L0 + (pos >> 5), 1u << (pos & 31u));
+            atomicOr(L1 + (pos >> 10), 1u << ((pos >> 5) & 31u));
         }
-        uint32_t n = cnt;
-        uint32_t age = cnt;
+        if (lane == 0) tail[g.seedpos[s0]] = (uint16_t)cnt;        // the seeds open the 0.0 group
         __syncwarp();
 
-        // pending buffer (warp-uniform) + per-slot node data (lanes 0..5, global-graph mode)
-        uint64_t pk[FLOOD_PS];
-        uint32_t plab[FLOOD_PS], pnb[FLOOD_PS], pkey[FLOOD_PS];
-#pragma unroll
-        for (int s = 0; s < FLOOD_PS; ++s) { pk[s] = EMPTY; plab[s] = 0; pnb[s] = NO_NODE32; pkey[s] = 0; }
-        uint64_t topk = heap[0];                                     // cached heap top (EMPTY = heap empty)
-        // data of the heap top (global-graph mode): requested as soon as the top is known
-        uint64_t hfor = EMPTY;
-        uint32_t hnb = NO_NODE32, hkey = 0, hlab = 0;
-        auto request_top = [&]() {
-            if (!GSMEM && topk != EMPTY && hfor != topk) {
-                const uint32_t node = (uint32_t)topk & 0xFFFFu;
-                hnb = NO_NODE32;
-                if (lane < 6) {
-                    hnb = __ldg(grec + (size_t)node * 12 + lane);
-                    hkey = __ldg(grec + (size_t)node * 12 + 6 + lane);
-                }
-                hlab = __ldcg(glab + node);
-                hfor = topk;
-            }
+        // asynchronous copy of a node record into this lane's staging slot
+        auto request = [&](uint32_t node) {
+            const uint4 *src = rec + 2u * node;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(my_stage), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(my_stage + 16u), "l"(src + 1) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        request_top();
+        auto back_insert = [&](uint32_t qq) {
+            atomicOr(L0 + (qq >> 5), 1u << (qq & 31u));
+            atomicOr(L1 + (qq >> 10), 1u << ((qq >> 5) & 31u));
+        };
+        uint32_t F = EMPTY;          // this lane's front entry
+        uint32_t bmin = 0;           // every back entry is >= bmin, every front entry < bmin
 #ifdef FLOOD_PROF
         unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long tc0 = clock64();
 #endif
-
         for (;;) {
-            // ---- minimum and maximum of the pending buffer (uniform, no communication) ----
-            uint64_t mP = EMPTY, xP = 0;
-            int sP = -1, tP = -1;
-#pragma unroll
-            for (int s = 0; s < FLOOD_PS; ++s) {
-                if (pk[s] < mP) { mP = pk[s]; sP = s; }
-                if (pk[s] != EMPTY && pk[s] >= xP) { xP = pk[s]; tP = s; }
-            }
-            if (mP == EMPTY && topk == EMPTY) break;
-            FP_ADD(0, 1);
-            uint32_t p, nb = NO_NODE32, kord = 0, labp = 0;
-            if (mP < topk) {
-                // ---- pop from the pending buffer ----
+            uint32_t mn = __reduce_min_sync(FULL, F);
+            if (mn == EMPTY) {
+                // ---- refill the front from the back: the first non-empty word and the 31 after it ----
                 FP_ADD(1, 1);
-                p = (uint32_t)mP & 0xFFFFu;
+                const uint32_t a = lane < n1 ? L1[lane] : 0u;
+                const uint32_t b = lane + 32u < n1 ? L1[lane + 32u] : 0u;
+                const unsigned ba = __ballot_sync(FULL, a != 0), bb = __ballot_sync(FULL, b != 0);
+                if ((ba | bb) == 0) break;                              // queue empty: component done
+                const uint32_t i2 = ba ? (uint32_t)__ffs((int)ba) - 1u : 32u + (uint32_t)__ffs((int)bb) - 1u;
+                const uint32_t w1 = __shfl_sync(FULL, ba ? a : b, i2 & 31u);
+                const uint32_t i1 = i2 * 32u + (uint32_t)__ffs((int)w1) - 1u;
+                const uint32_t wj = i1 + lane < n0 ? L0[i1 + lane] : 0u;
+                const uint32_t cj = (uint32_t)__popc(wj);
+                uint32_t sj = cj;                                        // inclusive prefix of the bit counts
 #pragma unroll
-                for (int s = 0; s < FLOOD_PS; ++s)
-                    if (s == sP) { nb = pnb[s]; kord = pkey[s]; labp = plab[s]; pk[s] = EMPTY; }
-            } else {
-                // ---- pop the heap top; the root is refilled with the largest pending entry
-                //      (or the last heap entry) and sifted down ----
-                p = (uint32_t)topk & 0xFFFFu;
-                request_top();
-                nb = hnb; kord = hkey; labp = hlab;
-                uint64_t ins;
-                if (tP >= 0) {
-                    ins = xP;
-#pragma unroll
-                    for (int s = 0; s < FLOOD_PS; ++s)
-                        if (s == tP) pk[s] = EMPTY;
-                } else {
-                    --n;
-                    ins = n > 0 ? heap[n] : EMPTY;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, sj, o);
+                    if (lane >= (unsigned)o) sj += t;
+                }
+                const bool take = sj <= 32u;                             // whole words only; lane 0 always fits
+                const unsigned tb = __ballot_sync(FULL, take);
+                const uint32_t k = (uint32_t)__ffs((int)~tb) - 1u;       // taken words = lanes [0, k)  (k = 32: ffs(0) - 1)
+                const uint32_t kk = tb == FULL ? 32u : k;
+                const uint32_t total = __shfl_sync(FULL, sj, kk - 1u);
+                if (lane < kk && wj) {
+                    uint32_t e = sj - cj, x = wj;
+                    while (x) {
+                        scratch[e++] = (i1 + lane) * 32u + (uint32_t)__ffs((int)x) - 1u;
+                        x &= x - 1u;
+                    }
+                    L0[i1 + lane] = 0u;
+                    atomicAnd(L1 + ((i1 + lane) >> 5), ~(1u << ((i1 + lane) & 31u)));
                 }
                 __syncwarp();
-                if (n == 0) {
-                    topk = EMPTY;
-                } else {
-                    uint32_t i = 0;
-                    bool top_known = false;
-                    for (;;) {
-                        const uint32_t c0 = i * 32u + 1u;
-                        if (c0 >= n) break;
-                        const uint32_t ch = c0 + lane;
-                        const uint64_t k = ch < n ? heap[ch] : EMPTY;
-                        const uint32_t hi = (uint32_t)(k >> 32);
-                        const uint32_t mhi = __reduce_min_sync(FULL, hi);
-                        const uint32_t lo = hi == mhi ? (uint32_t)k : 0xFFFFFFFFu;
-                        const uint32_t mlo = __reduce_min_sync(FULL, lo);
-                        const uint64_t mk = ((uint64_t)mhi << 32) | mlo;
-                        if (mk >= ins) break;
-                        const uint32_t win = __ffs(__ballot_sync(FULL, hi == mhi && lo == mlo)) - 1;
-                        if (lane == 0) heap[i] = mk;
-                        __syncwarp();
-                        if (!top_known) { topk = mk; top_known = true; request_top(); }
-                        i = c0 + win;
-                        FP_ADD(6, 1);
-                    }
-                    if (lane == 0) heap[i] = ins;
-                    __syncwarp();
-                    if (!top_known) { topk = ins; request_top(); }
+                if (lane < total) {
+                    const uint32_t pos = scratch[lane];
+                    const uint32_t node = slots[pos];
+                    F = (pos << 16) | node;
+                    request(node);
                 }
+                bmin = (i1 + kk) * 32u;
+                __syncwarp();
+                continue;
             }
-            // ---- expand the popped node (watershed.py:135-154) ---------------------
-            bool claim = false;
-            if (GSMEM) {
-                labp = slab[p];
-                if (lane < 6) { const uint32_t t = snbr[p * 6u + lane]; nb = t == NO_NODE ? NO_NODE32 : t; }
-                if (nb != NO_NODE32) {
-                    claim = slab[nb] == 0;
-                    // edge key: stored at the popped voxel for the three negative directions,
-                    // at the neighbour for the positive ones
-                    kord = skey[(lane < 3 ? p : nb) * 3u + axis];
-                }
-            } else {
-                if (nb != NO_NODE32) claim = ((sbits[nb >> 5] >> (nb & 31)) & 1u) == 0;
+            // ---- pop the lowest front entry -------------------------------------------
+            FP_ADD(0, 1);
+            const uint32_t o = (uint32_t)__ffs((int)__ballot_sync(FULL, F == mn)) - 1u;
+            if (lane == o) {
+                F = EMPTY;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
-            unsigned bits = __ballot_sync(FULL, claim);
-            if (claim) {                                  // labelled at push time (:149)
-                if (GSMEM) slab[nb] = labp;
-                else { atomicOr(sbits + (nb >> 5), 1u << (nb & 31)); __stcg(glab + nb, labp); }
-            }
-            const uint32_t myage = age + __popc(bits & ((1u << lane) - 1u));
-            const uint64_t mykey = ((uint64_t)kord << 32) | ((uint64_t)myage << 16) | (nb & 0xFFFFu);
-            age += __popc(bits);
-            FP_ADD(4, __popc(bits));
             __syncwarp();
-            // ---- queue the claimed neighbours ------------------------------------------
-            while (bits) {
-                const int src = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const uint64_t k = __shfl_sync(FULL, mykey, src);
-                int fs = -1;
-#pragma unroll
-                for (int s = FLOOD_PS - 1; s >= 0; --s)
-                    if (pk[s] == EMPTY) fs = s;
-                if (fs >= 0) {
-                    const uint32_t node = (uint32_t)k & 0xFFFFu;
-#pragma unroll
-                    for (int s = 0; s < FLOOD_PS; ++s)
-                        if (s == fs) {
-                            pk[s] = k;
-                            if (!GSMEM) {
-                                plab[s] = labp;
-                                pnb[s] = NO_NODE32;
-                                if (lane < 6) {
-                                    pnb[s] = __ldg(grec + (size_t)node * 12 + lane);
-                                    pkey[s] = __ldg(grec + (size_t)node * 12 + 6 + lane);
-                                }
-                            }
-                        }
-                } else {
-                    // pending buffer full: regular heap push
-                    FP_ADD(5, 1);
-                    uint32_t i = n++;
-                    while (i > 0) {
-                        const uint32_t par = (i - 1u) >> 5;
-                        const uint64_t pkv = heap[par];
-                        if (pkv <= k) break;
-                        if (lane == 0) heap[i] = pkv;
-                        i = par;
+            const uint32_t p = mn & 0xFFFFu;
+            // ---- expand (watershed.py:135-154): lanes 0..5 = neighbours [-z,-y,-x,+x,+y,+z] ----
+            const uint32_t labp = slab[p];
+            uint32_t nb = NO_NODE, gp = 0;
+            if (lane < 6) {
+                nb = stage16[o * 16u + lane];
+                gp = stage16[o * 16u + 6u + lane];
+            }
+            const bool claim = nb != NO_NODE && slab[nb] == 0;
+            const unsigned cb = __ballot_sync(FULL, claim);
+            if (cb == 0) continue;
+            uint32_t qq = 0;
+            if (claim) slab[nb] = (uint16_t)labp;                         // labelled at push time (:149)
+            if ((cb & (cb - 1u)) == 0) {                                   // one claim (the common case)
+                if (claim) {
+                    const uint32_t t = tail[gp];
+                    tail[gp] = (uint16_t)(t + 1u);
+                    qq = gp + t;
+                }
+            } else {                                                       // in direction order: equal values
+                for (unsigned rest = cb; rest; rest &= rest - 1u) {        // share a group
+                    if (lane == (unsigned)__ffs((int)rest) - 1u) {
+                        const uint32_t t = tail[gp];
+                        tail[gp] = (uint16_t)(t + 1u);
+                        qq = gp + t;
                     }
-                    if (lane == 0) heap[i] = k;
                     __syncwarp();
-                    if (i == 0) { topk = k; request_top(); }
                 }
             }
+            if (claim) slots[qq] = (uint16_t)nb;
+            const bool to_back = claim && qq >= bmin;
+            if (to_back) { back_insert(qq); FP_ADD(3, 1); }
+            unsigned fb = __ballot_sync(FULL, claim && qq < bmin);
+            const uint32_t x = (qq << 16) | nb;
+            while (fb) {
+                const int src = __ffs((int)fb) - 1;
+                fb &= fb - 1u;
+                const uint32_t xs = __shfl_sync(FULL, x, src);
+                const unsigned free_lanes = __ballot_sync(FULL, F == EMPTY);
+                if (free_lanes) {
+                    FP_ADD(2, 1);
+                    if (lane == (unsigned)__ffs((int)free_lanes) - 1u) {
+                        F = xs;
+                        request(xs & 0xFFFFu);
+                    }
+                } else {
+                    // front full: the larger of (new entry, front maximum) moves to the back
+                    FP_ADD(4, 1);
+                    const uint32_t mx = __reduce_max_sync(FULL, F);
+                    const uint32_t y = xs > mx ? xs : mx;
+                    if (mx > xs && F == mx) {
+                        F = xs;
+                        request(xs & 0xFFFFu);
+                    }
+                    if (lane == 0) back_insert(y >> 16);
+                    bmin = y >> 16;
+                }
+            }
+            __syncwarp();
         }
 #ifdef FLOOD_PROF
         if (lane == 0 && nv > 5000) {
-            prof[2] = (unsigned long long)(clock64() - tc0);
-            for (int q = 0; q < 7; ++q) atomicAdd(&g_flood_prof[GSMEM ? 1 : 0][q], prof[q]);
+            prof[6] = (unsigned long long)(clock64() - tc0);
+            for (int qi = 0; qi < 8; ++qi) atomicAdd(&g_flood_prof[qi], prof[qi]);
         }
 #endif
-        // ---- write the component's labels back ---------------------------------------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        for (uint32_t i = lane; i < nv; i += 32)
-            labels[cg.vox[b0 + i]] = GSMEM ? slab[i] : __ldcg(glab + i);
+        // ---- write the component's labels back ---------------------------------------
+        for (uint32_t i = lane; i < nv; i += 32) {
+            const uint32_t l = slab[i];
+            if (l) labels[g.vox[b0 + i]] = g.complab[s0 + l - 1u];
+        }
     }
+}
+
+static constexpr int EG_ITEMS = 8;
+struct MaxU32 {
+    __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+// One CTA per component: group starts of the sorted edge list, scattered into the node
+// records of both end points; queue positions of the seeds.
+__global__ void __launch_bounds__(256)
+edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__restrict__ ebase,
+                  const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ comp_start,
+                  const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+                  uint16_t *__restrict__ rec16, uint32_t *__restrict__ seedpos) {
+    typedef cub::BlockScan<uint32_t, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ uint32_t carry;
+    const uint32_t t = threadIdx.x;
+    for (uint32_t c = blockIdx.x; c < *n_comp_dev; c += gridDim.x) {
+        const uint32_t e0 = ebase[c], P = ebase[c + 1] - e0;
+        if (P == 0) continue;
+        const uint32_t b0 = cbase[c], s0 = comp_start[c];
+        __syncthreads();
+        if (t == 0) carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < P; base += 256 * EG_ITEMS) {
+            // blocked arrangement: thread t owns EG_ITEMS consecutive entries
+            const uint32_t i0 = base + t * EG_ITEMS;
+            uint32_t gs[EG_ITEMS];
+            uint32_t prev = (i0 > 0 && i0 - 1 < P) ? skeys[e0 + i0 - 1] : 0u;
+#pragma unroll
+            for (int u = 0; u < EG_ITEMS; ++u) {
+                const uint32_t i = i0 + u;
+                const uint32_t k = i < P ? skeys[e0 + i] : 0u;
+                gs[u] = (i > 0 && i < P && k != prev) ? i : 0u;
+                prev = k;
+            }
+            Scan(tmp).InclusiveScan(gs, gs, MaxU32());
+            const uint32_t cr = carry;
+            __syncthreads();
+            if (t == 255) carry = gs[EG_ITEMS - 1] > cr ? gs[EG_ITEMS - 1] : cr;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < EG_ITEMS; ++u) {
+                const uint32_t i = i0 + u;
+                if (i >= P) break;
+                const uint32_t start = gs[u] > cr ? gs[u] : cr;
+                const uint32_t id = svals[e0 + i];
+                if (id & BQ_SEED_FLAG) {
+                    seedpos[s0 + (id & ~BQ_SEED_FLAG)] = i;
+                } else {
+                    const uint32_t j = id / 3u, axis = id - 3u * j;
+                    const uint32_t nb = rec16[(size_t)(b0 + j) * 16u + axis];
+                    if (nb != NO_NODE) {      // edge (j, j - e_axis): same value from either side
+                        rec16[(size_t)(b0 + j) * 16u + 6u + axis] = (uint16_t)start;
+                        rec16[(size_t)(b0 + nb) * 16u + 6u + (5u - axis)] = (uint16_t)start;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// value-0.0 pseudo edges of the seeds, placed in front of the component's edge segment (the
+// radix sort is stable, so they open the 0.0 group in flat-index order)
+__global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_t n,
+                                 const uint32_t *__restrict__ comp_label,
+                                 const uint32_t *__restrict__ comp_start,
+                                 const uint32_t *__restrict__ ebase, uint32_t *__restrict__ ekeys,
+                                 uint32_t *__restrict__ evals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = seed_keys[i];
+    if (k == ~0ull) return;
+    const uint32_t cl = comp_label[(uint32_t)(k >> 32)];
+    if (!(cl & MULTI_FLAG)) return;
+    const uint32_t c = cl & ~MULTI_FLAG;
+    const uint32_t e0 = ebase[c];
+    if (ebase[c + 1] == e0) return;
+    const uint32_t idx = i - comp_start[c];
+    ekeys[e0 + idx] = f32_ord(0.0f);
+    evals[e0 + idx] = BQ_SEED_FLAG | idx;
 }
 
 // Pass 1 of the compaction, fused with the single-seed fill: every voxel of a
@@ -572,12 +587,17 @@ fill_assign_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restri
     }
 }
 
-// Pass 2: adjacency and edge keys of every compacted node.
+// Pass 2: adjacency and edge keys of every compacted node.  Components of the bucket-queue
+// classes get a 32-byte record per node and one (key, id) entry per stored edge in their
+// segment of the edge arena; class XL keeps the wide arrays of the heap kernel.
 __global__ void __launch_bounds__(256)
 compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
+                     const uint32_t *__restrict__ comp_label, const uint32_t *__restrict__ comp_start,
+                     const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ ebase,
                      const uint32_t *__restrict__ lidmap, const uint32_t *__restrict__ vox,
                      const uint32_t *__restrict__ total_dev, uint32_t *__restrict__ nbr,
-                     uint32_t *__restrict__ key, uint32_t *__restrict__ lab, uint32_t *__restrict__ rec) {
+                     uint32_t *__restrict__ key, uint32_t *__restrict__ lab, uint4 *__restrict__ rec,
+                     uint32_t *__restrict__ ekeys, uint32_t *__restrict__ evals) {
     const uint32_t total = *total_dev;
     const uint32_t plane = g.yp * g.xp;
     const uint64_t npix = (uint64_t)plane * g.zp;
@@ -585,31 +605,40 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
         const uint32_t v = vox[j];
         const uint32_t r = parent[v];
+        const uint32_t c = comp_label[r] & ~MULTI_FLAG;
         const uint32_t z = v / plane, rem = v - z * plane, y = rem / g.xp, x = rem - y * g.xp;
         const int64_t offs[6] = {-(int64_t)plane, -(int64_t)g.xp, -1, 1, (int64_t)g.xp, (int64_t)plane};
+        uint32_t id[6];
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
             const int64_t nb = (int64_t)v + offs[d];
-            uint32_t id = NO_NODE32;
-            if (nb >= 0 && (uint64_t)nb < npix && parent[nb] == r) id = lidmap[nb];
-            nbr[(size_t)j * 6 + d] = id;
-            rec[(size_t)j * 12 + d] = id;
+            id[d] = NO_NODE32;
+            if (nb >= 0 && (uint64_t)nb < npix && parent[nb] == r) id[d] = lidmap[nb];
         }
-        lab[j] = 0;
-        const uint32_t k0 = f32_ord(flood_key_value(g, 0, d0, g.scale[0], z, y, x));
-        const uint32_t k1 = f32_ord(flood_key_value(g, 1, d1, g.scale[1], z, y, x));
-        const uint32_t k2 = f32_ord(flood_key_value(g, 2, d2, g.scale[2], z, y, x));
-        key[(size_t)j * 3 + 0] = k0;
-        key[(size_t)j * 3 + 1] = k1;
-        key[(size_t)j * 3 + 2] = k2;
-        // all six edge keys of the node, in neighbour order [-z,-y,-x,+x,+y,+z]: the positive
-        // directions read the value stored at the neighbour
-        rec[(size_t)j * 12 + 6] = k0;
-        rec[(size_t)j * 12 + 7] = k1;
-        rec[(size_t)j * 12 + 8] = k2;
-        rec[(size_t)j * 12 + 9] = f32_ord(flood_key_value(g, 2, d2, g.scale[2], z, y, x + 1));
-        rec[(size_t)j * 12 + 10] = f32_ord(flood_key_value(g, 1, d1, g.scale[1], z, y + 1, x));
-        rec[(size_t)j * 12 + 11] = f32_ord(flood_key_value(g, 0, d0, g.scale[0], z + 1, y, x));
+        const uint32_t k[3] = {f32_ord(flood_key_value(g, 0, d0, g.scale[0], z, y, x)),
+                               f32_ord(flood_key_value(g, 1, d1, g.scale[1], z, y, x)),
+                               f32_ord(flood_key_value(g, 2, d2, g.scale[2], z, y, x))};
+        const uint32_t e0 = ebase[c];
+        if (ebase[c + 1] != e0) {
+            uint32_t h[6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) h[d] = id[d] == NO_NODE32 ? NO_NODE : id[d];
+            rec[(size_t)j * 2] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), 0u);
+            rec[(size_t)j * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t lid = j - cbase[c];
+            const uint32_t eb = e0 + (comp_start[c + 1] - comp_start[c]) + 3u * lid;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                ekeys[eb + a] = id[a] != NO_NODE32 ? k[a] : 0xFFFFFFFFu;
+                evals[eb + a] = 3u * lid + a;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 6; ++d) nbr[(size_t)j * 6 + d] = id[d];
+            lab[j] = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) key[(size_t)j * 3 + a] = k[a];
+        }
     }
 }
 

@@ -31,7 +31,14 @@ struct FloodStageBuffers {
     uint64_t *arena_keys;
     uint32_t *arena_idx;
     uint64_t arena_cap;
-    uint32_t *lidmap, *vox, *key, *nbr, *nlab, *rec;                  // compact component graphs
+    uint32_t *lidmap, *vox, *key, *nbr, *nlab;                   // compact component graphs
+    uint4 *rec;                                                  // bucket-queue node records
+    uint32_t *ebase;                                             // edge-arena segment per component
+    uint32_t *ekeys_a, *ekeys_b, *evals_a, *evals_b;             // edge arena (sort double buffers)
+    uint64_t edge_cap;
+    uint32_t *seedpos, *complab;
+    unsigned char *seg_tmp;
+    size_t seg_bytes;
 };
 
 // 6-connected components of the non-zero voxels of `dom` (padded volume):

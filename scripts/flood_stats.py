@@ -42,8 +42,7 @@ if hasattr(lib, 'isg_debug_flood_prof'):
     ws.segment_features_device(feats, labels)
     torch.cuda.synchronize()
     lib.isg_debug_flood_prof(buf, 0)
-    for k, name in ((1, 'smem graph (L)'), (0, 'global graph (G)')):
-        v = list(buf)[k * 8:(k + 1) * 8]
-        pops = max(v[0], 1)
-        print(f'{name}: comps>5000 nodes: pops {v[0]}  clk/pop {v[2]/pops:.0f}  pending-pops {v[1]/pops:.2f}'
-              f'  pushes/pop {v[4]/pops:.2f} spills/pop {v[5]/pops:.3f} sift levels/pop {v[6]/pops:.2f}')
+    v = list(buf)
+    pops = max(v[0], 1)
+    print(f'bucket-queue flood, comps > 5000 nodes: pops {v[0]}  clk/pop {v[6]/pops:.0f}; per pop: refills {v[1]/pops:.3f} '
+          f'front pushes {v[2]/pops:.2f} back pushes {v[3]/pops:.2f} evictions {v[4]/pops:.4f}')

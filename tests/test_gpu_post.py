@@ -61,18 +61,19 @@ def test_flood_random_vs_oracle(ws, shape, p, n, quant):
 
 @pytest.mark.parametrize('quant', [None, 4])
 def test_flood_size_classes(ws, quant):
-    """Disjoint boxes sized to hit every flood size class (shared-memory S / M / L and the
-    global-arena XL path), several seeds each, a duplicated seed and a seed outside the mask."""
+    """Disjoint boxes sized to hit every flood size class (bucket-queue S / M / L and the
+    heap-kernel XL path), several seeds each, a duplicated seed and a seed outside the mask."""
     from oracle import flood as oflood
     rng = np.random.default_rng(17 if quant else 18)
-    shape = (26, 120, 120)
+    shape = (30, 120, 120)
     aff = rng.random((3,) + shape, dtype=np.float32)
     if quant:
         aff = (np.round(aff * quant) / quant).astype(np.float32)
     mask = np.zeros(shape, bool)
     seeds = []
     boxes = [(1, 1, 1, 5), (1, 10, 1, 5), (1, 20, 1, 7), (1, 30, 1, 10), (1, 45, 1, 11),
-             (1, 60, 1, 16), (1, 80, 1, 18), (1, 1, 40, 20), (1, 30, 40, 24), (1, 60, 40, 3)]
+             (1, 60, 1, 16), (1, 80, 1, 18), (1, 1, 40, 20), (1, 30, 40, 24), (1, 60, 40, 3),
+             (1, 64, 70, 26)]
     for z0, y0, x0, e in boxes:
         mask[z0:z0 + e, y0:y0 + e, x0:x0 + e] = True
         k = 1 if e == 3 else int(rng.integers(2, 9))
