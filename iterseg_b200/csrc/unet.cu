@@ -86,7 +86,7 @@ static bool make_act_map(CUtensorMap *m, const void *base, int C, int W, int H, 
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                              (cuuint64_t)D * H * W * C * 2};
-    cuuint32_t box[5] = {(cuuint32_t)cblk, (cuuint32_t)P, (cuuint32_t)(Ht + 2), 3u, 1u};
+    cuuint32_t box[5] = {(cuuint32_t)cblk, (cuuint32_t)P, (cuuint32_t)(Ht + 2), 1u, 1u};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(base), dims,
                              strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -114,6 +114,7 @@ struct TcLayer {
     ConvGeom g;
     CUtensorMap tmA0, tmA1, tmB;
     int cblk;
+    int fold;
     size_t smem;
     int grid;
 };
@@ -152,7 +153,7 @@ static void choose_tile(int H, int W, int rb, int &P, int &Ht) {
         const int ht = 130 / p;
         if (ht < 1) continue;
         const int wt = p - 2;
-        if (3L * (ht + 2) * p * rb > 80 * 1024) continue;
+        if ((long)(ht + 2) * p * rb > 27 * 1024) continue;       // one plane slot
         const long tiles = (long)((W + wt - 1) / wt) * ((H + ht - 1) / ht);
         const long cost = tiles * 4096 + (long)(ht + 2) * p;      // fewest tiles, then smallest halo
         if (best < 0 || cost < best) {
@@ -219,45 +220,66 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     t.cblk = cblk;
     ConvGeom &g = t.g;
     g.N = p->N; g.D = p->D[l]; g.H = p->H[l]; g.W = p->W[l];
-    choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+    g.cout = cout_pad(i);
+    // thin, wide layers: fold the three dx taps into the MMA's N (needs P = 32: a patch row per warp)
+    const bool fold = g.cout <= 64 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
+    t.fold = fold ? 1 : 0;
+    if (fold) { g.P = 32; g.Ht = 4; }
+    else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+    g.acc_cols = fold ? 3 * g.cout : g.cout;
     g.Wt = g.P - 2;
     g.tiles_w = (g.W + g.Wt - 1) / g.Wt;
     g.tiles_h = (g.H + g.Ht - 1) / g.Ht;
-    g.n_tiles = g.N * g.D * g.tiles_h * g.tiles_w;
-    g.cout = cout_pad(i);
     g.nkb0 = c0 / cblk;
     g.nkb1 = c1 / cblk;
-    g.a_rows = 3 * (g.Ht + 2) * g.P;
-    g.a_stage_bytes = (g.a_rows * cblk * 2 + 1023) & ~1023;
-    // B ring: group G taps per stage so that a stage is <= 36 KB (fewer barrier round trips
-    // for the thin layers); A ring: as many stages as still fit (2..4)
+    const int nkb = g.nkb0 + g.nkb1;
+    g.plane_rows = (g.Ht + 2) * g.P;
+    g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
+    // T output planes per group: as many accumulators as TMEM holds (512 columns), balanced
+    // over the z extent; then the weight ring: everything resident if it fits, else G taps
+    // per stage (a stage <= 36 KB) and as many stages as fit (>= 2)
+    const long budget = 232448 - (1024 + CONV_SLACK + CONV_BAR_BYTES + 4 * 32 * 33 * 4);
     const int tap_bytes = g.cout * cblk * 2;
-    int G = 1;
-    for (int cand : {27, 9, 3, 1})
-        if (cand * tap_bytes <= 36 * 1024) { G = cand; break; }
-    g.taps_per_b = G;
-    g.b_stage_bytes = G * tap_bytes;
-    const long budget = 232448 - (1024 + CONV_SLACK + 512 + 4 * 32 * 33 * 4);
-    int nb = g.b_stage_bytes >= 24 * 1024 ? 2 : (g.b_stage_bytes >= 12 * 1024 ? 3 : 4);
-    if (27 / G < nb) nb = 27 / G < 2 ? 2 : 27 / G;
-    long na = (budget - (long)nb * g.b_stage_bytes) / g.a_stage_bytes;
-    if (na > 4) na = 4;
-    if (na < 2) {
+    int tmax = 512 / g.acc_cols;
+    if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
+    if (tmax > g.D) tmax = g.D;
+    bool placed = false;
+    for (; tmax >= 1 && !placed; --tmax) {
+        const int ngr = (g.D + tmax - 1) / tmax;
+        const int T = (g.D + ngr - 1) / ngr;
+        const long avail = budget - (long)(T + 2) * g.plane_bytes;
+        if (avail <= 0) continue;
+        if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
+            g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
+            g.b_resident = 1;
+            placed = true;
+            break;
+        }
+        for (int G : {9, 3, 1}) {
+            if (fold && G == 1) continue;
+            const long sb = (long)G * tap_bytes;
+            if (sb > 36 * 1024 && G > 1) continue;
+            long nb = avail / sb;
+            if (nb < 2) continue;
+            if (nb > 6) nb = 6;
+            g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
+            g.b_resident = 0;
+            placed = true;
+            break;
+        }
+    }
+    if (!placed) {
         set_error("conv %s: shared memory budget exceeded", CONVS[i].name);
         return false;
     }
-    // spend what is left on more B stages
-    long extra = (budget - na * g.a_stage_bytes - (long)nb * g.b_stage_bytes) / g.b_stage_bytes;
-    if (extra > 0) nb += (int)(extra > 4 ? 4 : extra);
-    if (nb > 16) nb = 16;
-    g.n_b_stages = nb;
-    g.n_a_stages = (int)na;
+    g.dgroups = (g.D + g.T - 1) / g.T;
+    g.n_groups = g.N * g.dgroups * g.tiles_h * g.tiles_w;
     g.out_mode = out_mode;
-    g.base_off_mode = p->base_off_mode;
+    { const char *dbg = getenv("ISG_CONV_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
     g.out = out;
     g.stats = p->stats[i];
     t.smem = conv_smem_bytes(g);
-    t.grid = g.n_tiles < num_sms() ? g.n_tiles : num_sms();
+    t.grid = g.n_groups < num_sms() ? g.n_groups : num_sms();
     if (!make_act_map(&t.tmA0, src0, c0, g.W, g.H, g.D, g.N, cblk, g.P, g.Ht)) return false;
     if (c1 > 0) {
         if (!make_act_map(&t.tmA1, src1, c1, g.W, g.H, g.D, g.N, cblk, g.P, g.Ht)) return false;
@@ -292,30 +314,32 @@ struct ProfScope {
     }
 };
 
-template <int CBLK, int G>
+template <int CBLK, int G, bool FOLD>
 static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
-    ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<CBLK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<CBLK, G, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)t.smem));
-    conv3d_tc_kernel<CBLK, G><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
+    conv3d_tc_kernel<CBLK, G, FOLD><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
     ISG_LAUNCHED();
     return ISG_OK;
 }
 
 static int launch_tc(const TcLayer &t, cudaStream_t st) {
     const int G = t.g.taps_per_b;
+    if (t.fold) {
+        if (t.cblk == 64) return G == 9 ? launch_tc_inst<64, 9, true>(t, st) : launch_tc_inst<64, 3, true>(t, st);
+        return G == 9 ? launch_tc_inst<32, 9, true>(t, st) : launch_tc_inst<32, 3, true>(t, st);
+    }
     if (t.cblk == 64) {
         switch (G) {
-            case 27: return launch_tc_inst<64, 27>(t, st);
-            case 9: return launch_tc_inst<64, 9>(t, st);
-            case 3: return launch_tc_inst<64, 3>(t, st);
-            default: return launch_tc_inst<64, 1>(t, st);
+            case 9: return launch_tc_inst<64, 9, false>(t, st);
+            case 3: return launch_tc_inst<64, 3, false>(t, st);
+            default: return launch_tc_inst<64, 1, false>(t, st);
         }
     }
     switch (G) {
-        case 27: return launch_tc_inst<32, 27>(t, st);
-        case 9: return launch_tc_inst<32, 9>(t, st);
-        case 3: return launch_tc_inst<32, 3>(t, st);
-        default: return launch_tc_inst<32, 1>(t, st);
+        case 9: return launch_tc_inst<32, 9, false>(t, st);
+        case 3: return launch_tc_inst<32, 3, false>(t, st);
+        default: return launch_tc_inst<32, 1, false>(t, st);
     }
 }
 

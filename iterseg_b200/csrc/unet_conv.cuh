@@ -4,21 +4,34 @@
 // (src/iterseg/unet.py:63-76 used at :93,:96); train-mode BatchNorm statistics
 // (unet.py:80-81) are reduced in the epilogue.
 //
-// Mapping (one CTA per SM, persistent over output tiles):
-//   M = 128 output voxels of one z-plane: a patch of Ht rows x P columns, linearised
-//       row-major with pitch P (the last 2 columns of every patch row are halo, so
-//       Wt = P-2 outputs per row are valid);
-//   N = Cout (16..256);  K = 27 taps x Cin, walked as (channel block of CBLK) x (tap).
-//   A: ONE TMA box per (tile, channel block): the halo patch {CBLK ch, P, Ht+2, 3 planes}
-//      of the channels-last activation tensor, out-of-bounds -> 0 (the conv padding).
-//      It lands in smem as rows of CBLK*2 bytes (hardware 128B/64B swizzle); every tap
-//      (dz,dy,dx) is the SAME smem tile read through a K-major UMMA descriptor whose
-//      start address is advanced by (dz*(Ht+2)*P + dy*P + dx) rows.  So each input
-//      voxel is fetched from L2 ~ (3*(Ht+2)*P)/(Ht*Wt) times instead of 27.
-//   B: weights packed [tap][Cout][Cin] fp16, one TMA box {CBLK, Cout} per (tap, block),
-//      streamed through its own ring.
-//   D: fp32 accumulators in TMEM, two stages of Cout columns (epilogue of tile i
-//      overlaps the MMAs of tile i+1).
+// Mapping (one CTA per SM, persistent over GROUPS of output tiles):
+//   tile : M = 128 output voxels of one z-plane: a patch of Ht rows x P columns, linearised
+//          row-major with pitch P (the last 2 columns of every patch row are halo, so
+//          Wt = P-2 outputs per row are valid);  N = Cout (16..256);
+//          K = 27 taps x Cin, walked as (channel block of CBLK) x (tap).
+//   group: T tiles stacked along z (same patch, output planes d0..d0+T-1), one fp32
+//          accumulator each in TMEM (T x Cout <= 512 columns).
+//   A: one TMA box per (input plane, channel block): the halo patch {CBLK ch, P, Ht+2} of the
+//      channels-last activation tensor, out-of-bounds -> 0 (the conv padding), landing in
+//      one of T+2 plane slots as rows of CBLK*2 bytes (hardware 128B/64B swizzle).  A group
+//      needs T+2 planes, so an input voxel is fetched from L2 ~ (T+2)/T * (Ht+2)*P/(Ht*Wt)
+//      times instead of 27; every tap (dz,dy,dx) of tile t is plane slot t+dz+1 read
+//      through a K-major UMMA descriptor whose start address is advanced by dy*P + dx rows.
+//   B: weights packed [tap][Cout][Cin] fp16, one TMA box {CBLK, Cout, G taps} per stage.
+//      The loop is WEIGHT-STATIONARY: a weight stage is used for all T tiles of the group
+//      before it is released, so the weight stream from L2 -- what bounded the previous,
+//      tile-at-a-time kernel (27*Cout*Cin*2 bytes per 128 voxels) -- shrinks T-fold; thin
+//      layers keep all their weights resident in shared memory.
+//   FOLD (thin layers, Cout <= 64 with P = 32): a tcgen05.mma costs >= ~45 clocks however small
+//      N is (measured, scripts/micro/umma_rate.cu), so with N = Cout = 32 the tensor pipe idles.
+//      The three dx taps of a (dz,dy) pair are therefore folded into N: one MMA with
+//      N = 3*Cout multiplies the un-shifted A view with the weights of dx = 0,1,2 (they are
+//      adjacent in the [tap][Cout][Cin] packing), and the epilogue adds the three column
+//      blocks with row shifts 0,1,2 -- out[r] = Y0[r] + Y1[r+1] + Y2[r+2] -- which are warp
+//      shuffles because a patch row is exactly one warp (P = 32; lanes 30,31 are halo).
+//      27 -> 9 MMAs per channel step.
+//   Plane slots and accumulators are released one by one at their last use, so the loads of
+//   the next channel block / group and the epilogue overlap the MMAs.
 // Warp roles: 0 = A producer, 3 = B producer, 1 = MMA issuer (one thread),
 //             2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> global + statistics).
 #pragma once
@@ -33,17 +46,21 @@ struct ConvGeom {
     int N, D, H, W;              // batch (chunks) and spatial extents (in == out)
     int P, Ht, Wt;               // patch pitch, patch rows, valid outputs per row
     int tiles_w, tiles_h;
-    int n_tiles;
-    int cout;                    // UMMA N (multiple of 16, <= 256)
+    int T;                       // output planes (accumulators) per group
+    int dgroups;                 // ceil(D / T)
+    int n_groups;                // N * dgroups * tiles_h * tiles_w
+    int cout;                    // output channels (multiple of 16, <= 256)
+    int acc_cols;                // TMEM columns per accumulator = UMMA N: cout, or 3 * cout when
+                                 // the three dx taps are folded into N (template parameter FOLD)
     int nkb0, nkb1;              // channel blocks taken from source 0 / source 1 (concat)
-    int a_rows;                  // 3 * (Ht + 2) * P
-    int a_stage_bytes;           // a_rows * CBLK * 2 rounded up to 1024
+    int plane_rows;              // (Ht + 2) * P
+    int plane_bytes;             // plane_rows * CBLK * 2 rounded up to 1024
     int b_stage_bytes;           // taps_per_b * cout * CBLK * 2
     int n_b_stages;
-    int n_a_stages;              // 2..4
-    int taps_per_b;              // taps per B stage (template parameter G): 1, 3, 9 or 27
+    int taps_per_b;              // taps per B stage (template parameter G): 1, 3 or 9
+    int b_resident;              // 1: all (nkb x 27/G) weight stages are loaded once and kept
     int out_mode;                // 0: fp16 [vox][cout]   1: fp32 [vox][8] (first 8 columns)
-    int base_off_mode;           // 0 (correct on B200): descriptor base_offset field = 0;  1: (addr >> 7) & 7
+    int debug;                   // ISG_CONV_DEBUG (diagnosis only): 1 skip epilogue body, 2 skip A loads, 4 skip B loads
     void *out;
     unsigned long long *stats;   // [N][cout][2] (sum, sum of squares) as 2^-24 fixed point:
                                  // integer atomics are order-independent -> reproducible
@@ -52,32 +69,37 @@ struct ConvGeom {
 static constexpr int CONV_THREADS = 256;
 static constexpr float STAT_SCALE = 16777216.0f;      // 2^24
 static constexpr int CONV_SLACK = 4096;      // garbage rows the last taps of invalid rows touch
+static constexpr int CONV_MAX_T = 10;
+static constexpr int CONV_MAX_B_STAGES = 24;
+static constexpr int CONV_BAR_BYTES = 1024;
 
 __host__ __device__ inline size_t conv_smem_bytes(const ConvGeom &g) {
-    return 1024 /* alignment */ + (size_t)g.n_a_stages * g.a_stage_bytes +
-           (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK + 512 /* barriers */ +
+    return 1024 /* alignment */ + (size_t)(g.T + 2) * g.plane_bytes +
+           (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK + CONV_BAR_BYTES +
            4 * 32 * 33 * sizeof(float);
 }
 
-template <int CBLK, int G>
+template <int CBLK, int G, bool FOLD>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvGeom g) {
     using namespace sm100;
     constexpr uint32_t RB = CBLK * 2;            // smem row bytes (128 -> SW128, 64 -> SW64)
     constexpr int KSTEPS = CBLK / 16;
+    constexpr int NBG = 27 / G;                  // weight stages per channel block
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t raw_base = smem_u32(smem_dyn);
     const uint32_t pad = ((raw_base + 1023u) & ~1023u) - raw_base;
     uint8_t *base = smem_dyn + pad;
     uint8_t *a_smem = base;
-    uint8_t *b_smem = a_smem + (size_t)g.n_a_stages * g.a_stage_bytes;
+    uint8_t *b_smem = a_smem + (size_t)(g.T + 2) * g.plane_bytes;
     uint8_t *tail = b_smem + (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
-    uint64_t *a_full = bars, *a_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10;
-    uint64_t *b_full = bars + 12, *b_empty = bars + 12 + 16;        // up to 16 B stages
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12 + 32);
-    float *stat_t = reinterpret_cast<float *>(tail + 512);
+    uint64_t *plane_full = bars, *plane_empty = bars + 12;
+    uint64_t *acc_full = bars + 24, *acc_empty = bars + 34;
+    uint64_t *b_full = bars + 44, *b_empty = bars + 44 + CONV_MAX_B_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44 + 2 * CONV_MAX_B_STAGES);
+    float *stat_t = reinterpret_cast<float *>(tail + CONV_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -89,11 +111,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < g.n_a_stages; ++i) {
-            mbar_init(&a_full[i], 1);
-            mbar_init(&a_empty[i], 1);
+        for (int i = 0; i < g.T + 2; ++i) {
+            mbar_init(&plane_full[i], 1);
+            mbar_init(&plane_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < g.T; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 4);
         }
@@ -112,41 +134,63 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // group index -> (patch column, patch row, z group, chunk)
+    auto decode = [&](int grp, int &wb, int &hb, int &d0, int &n, int &tg) {
+        int t = grp;
+        wb = t % g.tiles_w; t /= g.tiles_w;
+        hb = t % g.tiles_h; t /= g.tiles_h;
+        const int dg = t % g.dgroups;
+        n = t / g.dgroups;
+        d0 = dg * g.T;
+        tg = g.D - d0 < g.T ? g.D - d0 : g.T;
+    };
+
     if (warp == 0) {
         // ===================== A producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
-            const uint32_t na = (uint32_t)g.n_a_stages;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int wb = t % g.tiles_w; t /= g.tiles_w;
-                const int hb = t % g.tiles_h; t /= g.tiles_h;
-                const int d = t % g.D;
-                const int n = t / g.D;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % na, ph = (it / na) & 1u;
-                    mbar_wait(&a_empty[s], ph ^ 1u);
-                    mbar_expect_tx(&a_full[s], (uint32_t)g.a_rows * RB);
+            uint32_t ph = 0;                                  // per plane slot: uses so far (parity)
+            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+                int wb, hb, d0, n, tg;
+                decode(grp, wb, hb, d0, n, tg);
+                for (int kb = 0; kb < nkb; ++kb) {
                     const bool first = kb < g.nkb0;
-                    tma_load_5d(a_smem + (size_t)s * g.a_stage_bytes, first ? &tmA0 : &tmA1,
-                                &a_full[s], (first ? kb : kb - g.nkb0) * CBLK, wb * g.Wt - 1,
-                                hb * g.Ht - 1, d - 1, n);
+                    const CUtensorMap *tm = first ? &tmA0 : &tmA1;
+                    const int c = (first ? kb : kb - g.nkb0) * CBLK;
+                    for (int pi = 0; pi < tg + 2; ++pi) {
+                        mbar_wait(&plane_empty[pi], ((ph >> pi) & 1u) ^ 1u);
+                        if ((g.debug & 2) && grp != (int)blockIdx.x) { mbar_arrive(&plane_full[pi]); continue; }
+                        mbar_expect_tx(&plane_full[pi], (uint32_t)g.plane_rows * RB);
+                        tma_load_5d(a_smem + (size_t)pi * g.plane_bytes, tm, &plane_full[pi], c,
+                                    wb * g.Wt - 1, hb * g.Ht - 1, d0 - 1 + pi, n);
+                    }
+                    ph ^= (1u << (tg + 2)) - 1u;
                 }
             }
         }
     } else if (warp == 3) {
         // ===================== B producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
-            const uint32_t nb = (uint32_t)g.n_b_stages;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    for (int tap = 0; tap < 27; tap += G, ++it) {
-                        const uint32_t s = it % nb, ph = (it / nb) & 1u;
-                        mbar_wait(&b_empty[s], ph ^ 1u);
+            if (g.b_resident) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    for (int bg = 0; bg < NBG; ++bg) {
+                        const int s = kb * NBG + bg;
                         mbar_expect_tx(&b_full[s], (uint32_t)g.b_stage_bytes);
-                        tma_load_3d(b_smem + (size_t)s * g.b_stage_bytes, &tmB, &b_full[s],
-                                    kb * CBLK, 0, tap);
+                        tma_load_3d(b_smem + (size_t)s * g.b_stage_bytes, &tmB, &b_full[s], kb * CBLK, 0,
+                                    bg * G);
+                    }
+            } else {
+                uint32_t it = 0;
+                const uint32_t nb = (uint32_t)g.n_b_stages;
+                for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        for (int bg = 0; bg < NBG; ++bg, ++it) {
+                            const uint32_t s = it % nb, ph = (it / nb) & 1u;
+                            mbar_wait(&b_empty[s], ph ^ 1u);
+                            if ((g.debug & 4) && it >= nb) { mbar_arrive(&b_full[s]); continue; }
+                            mbar_expect_tx(&b_full[s], (uint32_t)g.b_stage_bytes);
+                            tma_load_3d(b_smem + (size_t)s * g.b_stage_bytes, &tmB, &b_full[s], kb * CBLK,
+                                        0, bg * G);
+                        }
                     }
                 }
             }
@@ -155,51 +199,81 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===================== MMA issuer =====================
         // One thread issues everything, so the instruction count per MMA is what bounds
         // small-N layers: descriptors are (constant high word) | (start address >> 4) and
-        // the tap loop is fully unrolled, leaving ~2 integer adds per tcgen05.mma.
+        // the tap loops are fully unrolled, leaving ~2 integer adds per tcgen05.mma.
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.cout, 0 /* fp16 */);
-            const uint32_t nb = (uint32_t)g.n_b_stages, na = (uint32_t)g.n_a_stages;
-            uint32_t ita = 0, itb = 0, tcount = 0;
+            const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.acc_cols, 0 /* fp16 */);
+            const uint32_t nb = (uint32_t)g.n_b_stages;
+            uint32_t itb = 0, plane_ph = 0, acc_ph = 0;
+            bool b_waited = false;
             const uint64_t dproto = make_kmajor_desc(0, RB, 0);
             const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
             constexpr uint32_t U = RB >> 4;                       // one row in 16-byte units
-            const uint32_t cz = (uint32_t)((g.Ht + 2) * g.P) * U, cy = (uint32_t)g.P * U;
+            const uint32_t cy = (uint32_t)g.P * U;
+            const uint32_t plane_units = (uint32_t)g.plane_bytes >> 4;
             const uint32_t b_tap_units = (uint32_t)(g.cout * CBLK * 2) >> 4;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
-                mbar_wait(&acc_empty[as], aph ^ 1u);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * (uint32_t)g.cout;
-                for (int kb = 0; kb < nkb; ++kb, ++ita) {
-                    const uint32_t s = ita % na, ph = (ita / na) & 1u;
-                    mbar_wait(&a_full[s], ph);
-                    const uint32_t a_lo = d_lo | (smem_u32(a_smem + (size_t)s * g.a_stage_bytes) >> 4);
-                    uint32_t b_lo = 0, bs = 0;
+            const uint32_t a_lo = d_lo | (smem_u32(a_smem) >> 4);
+            const uint32_t b_lo0 = d_lo | (smem_u32(b_smem) >> 4);
+            const uint32_t b_stage_units = (uint32_t)g.b_stage_bytes >> 4;
+            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+                int wb, hb, d0, n, tg;
+                decode(grp, wb, hb, d0, n, tg);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    int ready = 0;                                 // plane slots known to have landed
 #pragma unroll
-                    for (int tap = 0; tap < 27; ++tap) {
-                        if (tap % G == 0) {
+                    for (int bg = 0; bg < NBG; ++bg) {
+                        uint32_t bs;
+                        if (g.b_resident) {
+                            bs = (uint32_t)(kb * NBG + bg);
+                            if (!b_waited) mbar_wait(&b_full[bs], 0u);
+                        } else {
                             bs = itb % nb;
                             mbar_wait(&b_full[bs], (itb / nb) & 1u);
+                        }
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo0 + bs * b_stage_units;
+                        const int dz = (bg * G) / 9;               // G <= 9: one dz per stage
+                        for (int t = 0; t < tg; ++t) {
+                            if (kb == 0 && bg == 0) {
+                                mbar_wait(&acc_empty[t], ((acc_ph >> t) & 1u) ^ 1u);
+                                tc_fence_after();
+                            }
+                            while (ready <= t + dz) {
+                                mbar_wait(&plane_full[ready], (plane_ph >> ready) & 1u);
+                                ++ready;
+                            }
                             tc_fence_after();
-                            b_lo = d_lo | (smem_u32(b_smem + (size_t)bs * g.b_stage_bytes) >> 4);
-                        }
-                        const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
-                        const uint32_t a_tap = a_lo + dz * cz + dy * cy + dx * U;
-                        const uint32_t b_tap = b_lo + (tap % G) * b_tap_units;
+                            const uint32_t tmem_d = tmem_base + (uint32_t)(t * g.acc_cols);
+                            const uint32_t a_pl = a_lo + (uint32_t)(t + dz) * plane_units;
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k) {
-                            const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
-                            const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
-                            umma_f16(tmem_d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                            for (int j = 0; j < G; j += (FOLD ? 3 : 1)) {
+                                const int tap0 = bg * G;
+                                const int dy = ((tap0 + j) / 3) % 3, dx = (tap0 + j) % 3;   // FOLD: dx = 0
+                                const uint32_t a_tap = a_pl + dy * cy + dx * U;
+                                const uint32_t b_tap = b_lo + j * b_tap_units;
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
+                                    const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
+                                    umma_f16(tmem_d, adesc, bdesc, idesc,
+                                             (bg | j | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                                }
+                            }
+                            if (bg == NBG - 1) {
+                                umma_commit(&plane_empty[t + 2]);          // last use of plane t+2
+                                if (kb == nkb - 1) umma_commit(&acc_full[t]);
+                            }
                         }
-                        if (tap % G == G - 1) {
+                        if (bg == NBG / 3 - 1) umma_commit(&plane_empty[0]);       // end of the dz=-1 taps
+                        if (bg == 2 * NBG / 3 - 1) umma_commit(&plane_empty[1]);   // end of the dz=0 taps
+                        if (!g.b_resident) {
                             umma_commit(&b_empty[bs]);
                             ++itb;
                         }
                     }
-                    umma_commit(&a_empty[s]);
+                    plane_ph ^= (1u << (tg + 2)) - 1u;
                 }
-                umma_commit(&acc_full[as]);
+                b_waited = true;
+                acc_ph ^= (1u << tg) - 1u;
             }
         }
     } else if (warp >= 4) {
@@ -210,7 +284,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) csum[i] = csq[i] = 0;
         int cur_n = -1;
-        uint32_t tcount = 0;
         const int row = ew * 32 + lane;
         const int hy = row / g.P, wx = row - hy * g.P;
         auto flush = [&](int n) {
@@ -225,30 +298,47 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 csum[i] = csq[i] = 0;
             }
         };
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcount) {
-            int t = tile;
-            const int wb = t % g.tiles_w; t /= g.tiles_w;
-            const int hb = t % g.tiles_h; t /= g.tiles_h;
-            const int d = t % g.D;
-            const int n = t / g.D;
-            if (n != cur_n) {
-                flush(cur_n);
-                cur_n = n;
-            }
+        uint32_t acc_ph = 0;
+        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+          int wb, hb, d0, n, tg;
+          decode(grp, wb, hb, d0, n, tg);
+          if (n != cur_n) {
+              flush(cur_n);
+              cur_n = n;
+          }
+          for (int ti = 0; ti < tg; ++ti) {
+            const int d = d0 + ti;
             const int h = hb * g.Ht + hy, w = wb * g.Wt + wx;
             const bool valid = hy < g.Ht && wx < g.Wt && h < g.H && w < g.W;
             const size_t vox = (((size_t)n * g.D + d) * g.H + h) * g.W + w;
-            const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
-            mbar_wait(&acc_full[as], aph);
+            mbar_wait(&acc_full[ti], (acc_ph >> ti) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + as * (uint32_t)g.cout + ((uint32_t)(ew * 32) << 16);
+            if (g.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ti]);
+                continue;
+            }
+            const uint32_t taddr = tmem_base + (uint32_t)(ti * g.acc_cols) + ((uint32_t)(ew * 32) << 16);
             if (g.cout >= 32) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (i * 32 < g.cout) {
                         uint32_t v[32];
                         tmem_ld_32x32(taddr + i * 32, v);
-                        tmem_ld_wait();
+                        if (FOLD) {
+                            uint32_t v1[32], v2[32];
+                            tmem_ld_32x32(taddr + g.cout + i * 32, v1);
+                            tmem_ld_32x32(taddr + 2 * g.cout + i * 32, v2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = __float_as_uint(__uint_as_float(v[j]) +
+                                                       __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v1[j]), 1) +
+                                                       __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[j]), 2));
+                        } else {
+                            tmem_ld_wait();
+                        }
                         if (valid) {
                             __half *o = reinterpret_cast<__half *>(g.out) + vox * g.cout + i * 32;
 #pragma unroll
@@ -282,7 +372,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             } else {
                 uint32_t v[16];
                 tmem_ld_32x16(taddr, v);
-                tmem_ld_wait();
+                if (FOLD) {
+                    uint32_t v1[16], v2[16];
+                    tmem_ld_32x16(taddr + g.cout, v1);
+                    tmem_ld_32x16(taddr + 2 * g.cout, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) +
+                                               __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v1[j]), 1) +
+                                               __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[j]), 2));
+                } else {
+                    tmem_ld_wait();
+                }
                 if (valid) {
                     float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + vox * 8);
                     o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
@@ -308,7 +410,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (lane == 0) mbar_arrive(&acc_empty[ti]);
+          }
+          acc_ph ^= (1u << tg) - 1u;
         }
         flush(cur_n);
     }
