@@ -197,10 +197,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // One thread issues everything, so the instruction count per MMA is what bounds
-        // small-N layers: descriptors are (constant high word) | (start address >> 4) and
-        // the tap loops are fully unrolled, leaving ~2 integer adds per tcgen05.mma.
-        if (lane == 0) {
+        // The whole warp walks the loops (so that all the address arithmetic is warp-uniform)
+        // and one elected lane issues; what bounds thin layers is the instruction count per
+        // tcgen05.mma: descriptors are (constant high word) | (start address >> 4) and the tap
+        // loops are fully unrolled, leaving ~2 integer adds per MMA.
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.acc_cols, 0 /* fp16 */);
             const uint32_t nb = (uint32_t)g.n_b_stages;
             uint32_t itb = 0, plane_ph = 0, acc_ph = 0;
@@ -229,14 +231,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             bs = itb % nb;
                             mbar_wait(&b_full[bs], (itb / nb) & 1u);
                         }
-                        tc_fence_after();
                         const uint32_t b_lo = b_lo0 + bs * b_stage_units;
                         const int dz = (bg * G) / 9;               // G <= 9: one dz per stage
                         for (int t = 0; t < tg; ++t) {
-                            if (kb == 0 && bg == 0) {
-                                mbar_wait(&acc_empty[t], ((acc_ph >> t) & 1u) ^ 1u);
-                                tc_fence_after();
-                            }
+                            if (kb == 0 && bg == 0) mbar_wait(&acc_empty[t], ((acc_ph >> t) & 1u) ^ 1u);
                             while (ready <= t + dz) {
                                 mbar_wait(&plane_full[ready], (plane_ph >> ready) & 1u);
                                 ++ready;
@@ -244,31 +242,34 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             tc_fence_after();
                             const uint32_t tmem_d = tmem_base + (uint32_t)(t * g.acc_cols);
                             const uint32_t a_pl = a_lo + (uint32_t)(t + dz) * plane_units;
+                            if (leader) {
 #pragma unroll
-                            for (int j = 0; j < G; j += (FOLD ? 3 : 1)) {
-                                const int tap0 = bg * G;
-                                const int dy = ((tap0 + j) / 3) % 3, dx = (tap0 + j) % 3;   // FOLD: dx = 0
-                                const uint32_t a_tap = a_pl + dy * cy + dx * U;
-                                const uint32_t b_tap = b_lo + j * b_tap_units;
+                                for (int j = 0; j < G; j += (FOLD ? 3 : 1)) {
+                                    const int tap0 = bg * G;
+                                    const int dy = ((tap0 + j) / 3) % 3, dx = (tap0 + j) % 3;   // FOLD: dx = 0
+                                    const uint32_t a_tap = a_pl + dy * cy + dx * U;
+                                    const uint32_t b_tap = b_lo + j * b_tap_units;
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
-                                    const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
-                                    umma_f16(tmem_d, adesc, bdesc, idesc,
-                                             (bg | j | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                                    for (int k = 0; k < KSTEPS; ++k) {
+                                        const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
+                                        const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
+                                        umma_f16(tmem_d, adesc, bdesc, idesc,
+                                                 (bg | j | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                                    }
+                                }
+                                if (bg == NBG - 1) {
+                                    umma_commit(&plane_empty[t + 2]);          // last use of plane t+2
+                                    if (kb == nkb - 1) umma_commit(&acc_full[t]);
                                 }
                             }
-                            if (bg == NBG - 1) {
-                                umma_commit(&plane_empty[t + 2]);          // last use of plane t+2
-                                if (kb == nkb - 1) umma_commit(&acc_full[t]);
-                            }
                         }
-                        if (bg == NBG / 3 - 1) umma_commit(&plane_empty[0]);       // end of the dz=-1 taps
-                        if (bg == 2 * NBG / 3 - 1) umma_commit(&plane_empty[1]);   // end of the dz=0 taps
-                        if (!g.b_resident) {
-                            umma_commit(&b_empty[bs]);
-                            ++itb;
+                        if (leader) {
+                            if (bg == NBG / 3 - 1) umma_commit(&plane_empty[0]);       // end of the dz=-1 taps
+                            if (bg == 2 * NBG / 3 - 1) umma_commit(&plane_empty[1]);   // end of the dz=0 taps
+                            if (!g.b_resident) umma_commit(&b_empty[bs]);
                         }
+                        if (!g.b_resident) ++itb;
+                        __syncwarp();
                     }
                     plane_ph ^= (1u << (tg + 2)) - 1u;
                 }
