@@ -221,57 +221,71 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     ConvGeom &g = t.g;
     g.N = p->N; g.D = p->D[l]; g.H = p->H[l]; g.W = p->W[l];
     g.cout = cout_pad(i);
-    // thin, wide layers: fold the three dx taps into the MMA's N (needs P = 32: a patch row per warp)
-    const bool fold = g.cout <= 64 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
-    t.fold = fold ? 1 : 0;
-    if (fold) { g.P = 32; g.Ht = 4; }
-    else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
-    g.acc_cols = fold ? 3 * g.cout : g.cout;
-    g.Wt = g.P - 2;
-    g.tiles_w = (g.W + g.Wt - 1) / g.Wt;
-    g.tiles_h = (g.H + g.Ht - 1) / g.Ht;
     g.nkb0 = c0 / cblk;
     g.nkb1 = c1 / cblk;
     const int nkb = g.nkb0 + g.nkb1;
-    g.plane_rows = (g.Ht + 2) * g.P;
-    g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
-    // T output planes per group: as many accumulators as TMEM holds (512 columns), balanced
-    // over the z extent; then the weight ring: everything resident if it fits, else G taps
-    // per stage (a stage <= 36 KB) and as many stages as fit (>= 2)
     const long budget = 232448 - (1024 + CONV_SLACK + CONV_BAR_BYTES + 4 * 32 * 33 * 4);
     const int tap_bytes = g.cout * cblk * 2;
-    int tmax = 512 / g.acc_cols;
-    if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
-    if (tmax > g.D) tmax = g.D;
+    // Candidate configurations, best first:
+    //   fold    : the three dx taps folded into the MMA's N (thin, wide layers; needs P = 32, a
+    //             patch row per warp), two accumulator sets;
+    //   plain   : N = Cout; two accumulator sets (the epilogue of a group overlaps the next
+    //             group's MMAs) except for Cout = 256, where one set of T = 2 keeps the weight
+    //             stream from L2 halved.
+    // Per candidate: T output planes per group = as many accumulators as the set holds, balanced
+    // over the z extent; then the weight ring: everything resident if it fits, else G taps per
+    // stage (a stage <= 36 KB) and as many stages as fit (>= 2).
+    const bool want_fold = g.cout <= 64 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
     bool placed = false;
-    for (; tmax >= 1 && !placed; --tmax) {
-        const int ngr = (g.D + tmax - 1) / tmax;
-        const int T = (g.D + ngr - 1) / ngr;
-        const long avail = budget - (long)(T + 2) * g.plane_bytes;
-        if (avail <= 0) continue;
-        if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
-            g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
-            g.b_resident = 1;
-            placed = true;
-            break;
-        }
-        for (int G : {9, 3, 1}) {
-            if (fold && G == 1) continue;
-            const long sb = (long)G * tap_bytes;
-            if (sb > 36 * 1024 && G > 1) continue;
-            long nb = avail / sb;
-            if (nb < 2) continue;
-            if (nb > 6) nb = 6;
-            g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
-            g.b_resident = 0;
-            placed = true;
-            break;
+    for (int cand = want_fold ? 0 : 1; cand < 2 && !placed; ++cand) {
+        const bool fold = cand == 0;
+        const int acc = fold ? 3 * g.cout : g.cout;
+        const int nsets = (!fold && g.cout >= 256) ? 1 : 2;
+        int tmax = (512 / nsets) / acc;
+        if (tmax < 1) continue;
+        if (fold) { g.P = 32; g.Ht = 4; }
+        else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+        g.plane_rows = (g.Ht + 2) * g.P;
+        g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
+        if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
+        if (tmax > g.D) tmax = g.D;
+        for (; tmax >= 1 && !placed; --tmax) {
+            const int ngr = (g.D + tmax - 1) / tmax;
+            const int T = (g.D + ngr - 1) / ngr;
+            const long avail = budget - (long)(T + 2) * g.plane_bytes;
+            if (avail <= 0) continue;
+            if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
+                g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
+                g.b_resident = 1;
+                placed = true;
+            } else if (!fold || T >= 2) {
+                for (int G : {9, 3, 1}) {
+                    if (fold && G == 1) continue;
+                    const long sb = (long)G * tap_bytes;
+                    if (sb > 36 * 1024 && G > 1) continue;
+                    long nb = avail / sb;
+                    if (nb < 2) continue;
+                    if (nb > 6) nb = 6;
+                    g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
+                    g.b_resident = 0;
+                    placed = true;
+                    break;
+                }
+            }
+            if (placed) {
+                g.nsets = nsets;
+                g.acc_cols = acc;
+                t.fold = fold ? 1 : 0;
+            }
         }
     }
     if (!placed) {
         set_error("conv %s: shared memory budget exceeded", CONVS[i].name);
         return false;
     }
+    g.Wt = g.P - 2;
+    g.tiles_w = (g.W + g.Wt - 1) / g.Wt;
+    g.tiles_h = (g.H + g.Ht - 1) / g.Ht;
     g.dgroups = (g.D + g.T - 1) / g.T;
     g.n_groups = g.N * g.dgroups * g.tiles_h * g.tiles_w;
     g.out_mode = out_mode;

@@ -47,6 +47,8 @@ struct ConvGeom {
     int P, Ht, Wt;               // patch pitch, patch rows, valid outputs per row
     int tiles_w, tiles_h;
     int T;                       // output planes (accumulators) per group
+    int nsets;                   // 1: one accumulator set; 2: groups alternate between two sets, so the
+                                 // epilogue of a group overlaps the MMAs of the next one
     int dgroups;                 // ceil(D / T)
     int n_groups;                // N * dgroups * tiles_h * tiles_w
     int cout;                    // output channels (multiple of 16, <= 256)
@@ -96,9 +98,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint8_t *tail = b_smem + (size_t)g.n_b_stages * g.b_stage_bytes + CONV_SLACK;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
     uint64_t *plane_full = bars, *plane_empty = bars + 12;
-    uint64_t *acc_full = bars + 24, *acc_empty = bars + 34;
-    uint64_t *b_full = bars + 44, *b_empty = bars + 44 + CONV_MAX_B_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44 + 2 * CONV_MAX_B_STAGES);
+    uint64_t *acc_full = bars + 24, *acc_empty = bars + 44;            // [nsets * T] <= 20 each
+    uint64_t *b_full = bars + 64, *b_empty = bars + 64 + CONV_MAX_B_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 64 + 2 * CONV_MAX_B_STAGES);
     float *stat_t = reinterpret_cast<float *>(tail + CONV_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
@@ -115,7 +117,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(&plane_full[i], 1);
             mbar_init(&plane_empty[i], 1);
         }
-        for (int i = 0; i < g.T; ++i) {
+        for (int i = 0; i < g.T * g.nsets; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 4);
         }
@@ -216,9 +218,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t a_lo = d_lo | (smem_u32(a_smem) >> 4);
             const uint32_t b_lo0 = d_lo | (smem_u32(b_smem) >> 4);
             const uint32_t b_stage_units = (uint32_t)g.b_stage_bytes >> 4;
-            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+            uint32_t gcount = 0;
+            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++gcount) {
                 int wb, hb, d0, n, tg;
                 decode(grp, wb, hb, d0, n, tg);
+                const int a0 = g.nsets == 2 ? (int)(gcount & 1u) * g.T : 0;   // accumulator set of this group
                 for (int kb = 0; kb < nkb; ++kb) {
                     int ready = 0;                                 // plane slots known to have landed
 #pragma unroll
@@ -234,13 +238,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const uint32_t b_lo = b_lo0 + bs * b_stage_units;
                         const int dz = (bg * G) / 9;               // G <= 9: one dz per stage
                         for (int t = 0; t < tg; ++t) {
-                            if (kb == 0 && bg == 0) mbar_wait(&acc_empty[t], ((acc_ph >> t) & 1u) ^ 1u);
+                            if (kb == 0 && bg == 0) mbar_wait(&acc_empty[a0 + t], ((acc_ph >> (a0 + t)) & 1u) ^ 1u);
                             while (ready <= t + dz) {
                                 mbar_wait(&plane_full[ready], (plane_ph >> ready) & 1u);
                                 ++ready;
                             }
                             tc_fence_after();
-                            const uint32_t tmem_d = tmem_base + (uint32_t)(t * g.acc_cols);
+                            const uint32_t tmem_d = tmem_base + (uint32_t)((a0 + t) * g.acc_cols);
                             const uint32_t a_pl = a_lo + (uint32_t)(t + dz) * plane_units;
                             if (leader) {
 #pragma unroll
@@ -259,7 +263,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 }
                                 if (bg == NBG - 1) {
                                     umma_commit(&plane_empty[t + 2]);          // last use of plane t+2
-                                    if (kb == nkb - 1) umma_commit(&acc_full[t]);
+                                    if (kb == nkb - 1) umma_commit(&acc_full[a0 + t]);
                                 }
                             }
                         }
@@ -274,7 +278,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     plane_ph ^= (1u << (tg + 2)) - 1u;
                 }
                 b_waited = true;
-                acc_ph ^= (1u << tg) - 1u;
+                acc_ph ^= ((1u << tg) - 1u) << a0;
             }
         }
     } else if (warp >= 4) {
@@ -299,10 +303,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 csum[i] = csq[i] = 0;
             }
         };
-        uint32_t acc_ph = 0;
-        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+        uint32_t acc_ph = 0, gcount = 0;
+        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++gcount) {
           int wb, hb, d0, n, tg;
           decode(grp, wb, hb, d0, n, tg);
+          const int a0 = g.nsets == 2 ? (int)(gcount & 1u) * g.T : 0;
           if (n != cur_n) {
               flush(cur_n);
               cur_n = n;
@@ -312,15 +317,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int h = hb * g.Ht + hy, w = wb * g.Wt + wx;
             const bool valid = hy < g.Ht && wx < g.Wt && h < g.H && w < g.W;
             const size_t vox = (((size_t)n * g.D + d) * g.H + h) * g.W + w;
-            mbar_wait(&acc_full[ti], (acc_ph >> ti) & 1u);
+            mbar_wait(&acc_full[a0 + ti], (acc_ph >> (a0 + ti)) & 1u);
             tc_fence_after();
             if (g.debug & 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ti]);
+                if (lane == 0) mbar_arrive(&acc_empty[a0 + ti]);
                 continue;
             }
-            const uint32_t taddr = tmem_base + (uint32_t)(ti * g.acc_cols) + ((uint32_t)(ew * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)((a0 + ti) * g.acc_cols) + ((uint32_t)(ew * 32) << 16);
             if (g.cout >= 32) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -411,9 +416,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ti]);
+            if (lane == 0) mbar_arrive(&acc_empty[a0 + ti]);
           }
-          acc_ph ^= (1u << tg) - 1u;
+          acc_ph ^= ((1u << tg) - 1u) << a0;
         }
         flush(cur_n);
     }
