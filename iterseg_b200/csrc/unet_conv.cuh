@@ -207,7 +207,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const bool leader = elect_one();
             const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.acc_cols, 0 /* fp16 */);
             const uint32_t nb = (uint32_t)g.n_b_stages;
-            uint32_t itb = 0, plane_ph = 0, acc_ph = 0;
+            uint32_t plane_ph = 0, acc_ph = 0;
             bool b_waited = false;
             const uint64_t dproto = make_kmajor_desc(0, RB, 0);
             const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
@@ -218,34 +218,76 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t a_lo = d_lo | (smem_u32(a_smem) >> 4);
             const uint32_t b_lo0 = d_lo | (smem_u32(b_smem) >> 4);
             const uint32_t b_stage_units = (uint32_t)g.b_stage_bytes >> 4;
-            uint32_t gcount = 0;
-            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++gcount) {
-                int wb, hb, d0, n, tg;
-                decode(grp, wb, hb, d0, n, tg);
-                const int a0 = g.nsets == 2 ? (int)(gcount & 1u) * g.T : 0;   // accumulator set of this group
+            const uint32_t acc_cols = (uint32_t)g.acc_cols;
+            const int T = g.T, D = g.D, nsets = g.nsets, n_groups = g.n_groups, b_resident = g.b_resident;
+            const int gstride = (int)gridDim.x;
+            const int dgroups = g.dgroups, tiles_hw = g.tiles_h * g.tiles_w;
+            uint32_t gcount = 0, bs = 0, bph = 0;                  // weight ring position / parity
+            for (int grp = blockIdx.x; grp < n_groups; grp += gstride, ++gcount) {
+                const int dg = (grp / tiles_hw) % dgroups;
+                const int d0 = dg * T;
+                const int tg = D - d0 < T ? D - d0 : T;
+                const int a0 = nsets == 2 ? (int)(gcount & 1u) * T : 0;   // accumulator set of this group
+                const uint32_t tmem_g = tmem_base + (uint32_t)a0 * acc_cols;
+                if (b_resident) {
+                    // ---- tile-major: all taps of a tile back to back (weights never move) ----
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        int ready = 0;                             // plane slots known to have landed
+                        uint32_t tmem_d = tmem_g, a_pl = a_lo;
+                        for (int t = 0; t < tg; ++t, tmem_d += acc_cols, a_pl += plane_units) {
+                            if (kb == 0) mbar_wait(&acc_empty[a0 + t], ((acc_ph >> (a0 + t)) & 1u) ^ 1u);
+                            while (ready <= t + 2) {
+                                mbar_wait(&plane_full[ready], (plane_ph >> ready) & 1u);
+                                ++ready;
+                            }
+                            if (!b_waited)
+                                for (int bg = 0; bg < NBG; ++bg) mbar_wait(&b_full[kb * NBG + bg], 0u);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t b_kb = b_lo0 + (uint32_t)(kb * NBG) * b_stage_units;
+#pragma unroll
+                                for (int tap = 0; tap < 27; tap += (FOLD ? 3 : 1)) {
+                                    const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;   // FOLD: dx = 0
+                                    const uint32_t a_tap = a_pl + dz * plane_units + dy * cy + dx * U;
+                                    const uint32_t b_tap = b_kb + (tap / G) * b_stage_units + (tap % G) * b_tap_units;
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) {
+                                        const uint64_t adesc = ((uint64_t)d_hi << 32) | (a_tap + 2 * k);
+                                        const uint64_t bdesc = ((uint64_t)d_hi << 32) | (b_tap + 2 * k);
+                                        umma_f16(tmem_d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                                    }
+                                }
+                                umma_commit(&plane_empty[t]);                 // last use of plane t
+                                if (t == tg - 1) {
+                                    umma_commit(&plane_empty[tg]);
+                                    umma_commit(&plane_empty[tg + 1]);
+                                }
+                                if (kb == nkb - 1) umma_commit(&acc_full[a0 + t]);
+                            }
+                            __syncwarp();
+                        }
+                        b_waited = b_waited || kb == nkb - 1;
+                        plane_ph ^= (1u << (tg + 2)) - 1u;
+                    }
+                    acc_ph ^= ((1u << tg) - 1u) << a0;
+                    continue;
+                }
+                // ---- weight-stationary: a weight stage serves all tiles of the group ----
                 for (int kb = 0; kb < nkb; ++kb) {
-                    int ready = 0;                                 // plane slots known to have landed
+                    int ready = 0;
 #pragma unroll
                     for (int bg = 0; bg < NBG; ++bg) {
-                        uint32_t bs;
-                        if (g.b_resident) {
-                            bs = (uint32_t)(kb * NBG + bg);
-                            if (!b_waited) mbar_wait(&b_full[bs], 0u);
-                        } else {
-                            bs = itb % nb;
-                            mbar_wait(&b_full[bs], (itb / nb) & 1u);
-                        }
+                        mbar_wait(&b_full[bs], bph);
                         const uint32_t b_lo = b_lo0 + bs * b_stage_units;
                         const int dz = (bg * G) / 9;               // G <= 9: one dz per stage
-                        for (int t = 0; t < tg; ++t) {
+                        uint32_t tmem_d = tmem_g, a_pl = a_lo + (uint32_t)dz * plane_units;
+                        for (int t = 0; t < tg; ++t, tmem_d += acc_cols, a_pl += plane_units) {
                             if (kb == 0 && bg == 0) mbar_wait(&acc_empty[a0 + t], ((acc_ph >> (a0 + t)) & 1u) ^ 1u);
                             while (ready <= t + dz) {
                                 mbar_wait(&plane_full[ready], (plane_ph >> ready) & 1u);
                                 ++ready;
                             }
                             tc_fence_after();
-                            const uint32_t tmem_d = tmem_base + (uint32_t)((a0 + t) * g.acc_cols);
-                            const uint32_t a_pl = a_lo + (uint32_t)(t + dz) * plane_units;
                             if (leader) {
 #pragma unroll
                                 for (int j = 0; j < G; j += (FOLD ? 3 : 1)) {
@@ -270,14 +312,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         if (leader) {
                             if (bg == NBG / 3 - 1) umma_commit(&plane_empty[0]);       // end of the dz=-1 taps
                             if (bg == 2 * NBG / 3 - 1) umma_commit(&plane_empty[1]);   // end of the dz=0 taps
-                            if (!g.b_resident) umma_commit(&b_empty[bs]);
+                            umma_commit(&b_empty[bs]);
                         }
-                        if (!g.b_resident) ++itb;
+                        if (++bs == nb) { bs = 0; bph ^= 1u; }
                         __syncwarp();
                     }
                     plane_ph ^= (1u << (tg + 2)) - 1u;
                 }
-                b_waited = true;
                 acc_ph ^= ((1u << tg) - 1u) << a0;
             }
         }
