@@ -380,7 +380,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     auto vox = [&](int l) { return (size_t)p->D[l] * p->H[l] * p->W[l]; };
     ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
     // ---- c0.conv0 (CUDA cores, straight from the frame) ----
-    conv_in_kernel<<<egrid(vox(0), N), 256, 0, st>>>(frame, p->Z, p->Y, p->X, p->starts,
+    conv_in_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(frame, p->Z, p->Y, p->X, p->starts,
                                                      reinterpret_cast<const float *>(pk + L.w[0]),
                                                      p->raw[0], p->stats[0], p->D[0], p->H[0], p->W[0]);
     ISG_LAUNCHED();
@@ -446,7 +446,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         }
     }
     // ---- c8_0.conv1 (5 -> 5) + BN + sigmoid + placement ----
-    conv_out_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw8, p->stats[16], G(16), B(16),
+    conv_out_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(p->raw8, p->stats[16], G(16), B(16),
                                                       reinterpret_cast<const float *>(pk + L.w[17]),
                                                       p->raw9, p->stats[17], p->D[0], p->H[0], p->W[0]);
     ISG_LAUNCHED();

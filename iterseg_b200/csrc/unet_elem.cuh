@@ -209,49 +209,79 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], unsigned lon
 // c0.conv0: Cin = 1 -> 32, fp32 CUDA cores, reads the chunk straight out of the frame
 // (zero padding at the CHUNK border, as the reference pads the sliced chunk).
 // starts: [N][3] chunk origins.  grid = (blocks, N), block 256.
+// Each thread computes CONV_VX consecutive x voxels, so that a weight read from shared memory
+// (one LDS.128 = 4 channels) feeds CONV_VX FMAs per channel instead of one.
+static constexpr int CONV_VX = 4;
+
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *__restrict__ starts,
                const float *__restrict__ wgt /* [27][32] */, __half *__restrict__ raw,
                unsigned long long *__restrict__ stats, int D, int H, int W) {
-    __shared__ float w_s[27 * 32];
+    __shared__ __align__(16) float w_s[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) w_s[i] = wgt[i];
     __syncthreads();
     const int n = blockIdx.y;
     const int z0 = starts[n * 3 + 0], y0 = starts[n * 3 + 1], x0 = starts[n * 3 + 2];
     const size_t vox = (size_t)D * H * W;
+    const int wq = (W + CONV_VX - 1) / CONV_VX;
+    const size_t units = (size_t)D * H * wq;
     float ssum[32], ssq[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.0f;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vox;
-         v += (size_t)gridDim.x * blockDim.x) {
-        const int w = (int)(v % W);
-        const size_t t = v / W;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units;
+         u += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(u % wq) * CONV_VX;
+        const size_t t = u / wq;
         const int h = (int)(t % H);
         const int d = (int)(t / H);
-        float acc[32];
+        float acc[CONV_VX][32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+        for (int j = 0; j < CONV_VX; ++j)
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-            const int dd = d + tap / 9 - 1, hh = h + (tap / 3) % 3 - 1, ww = w + tap % 3 - 1;
-            float x = 0.0f;
-            if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
-                x = __ldg(frame + ((size_t)(z0 + dd) * Y + (y0 + hh)) * X + (x0 + ww));
+            for (int c = 0; c < 32; ++c) acc[j][c] = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, w_s[tap * 32 + c], acc[c]);
+        for (int zy = 0; zy < 9; ++zy) {
+            const int dd = d + zy / 3 - 1, hh = h + zy % 3 - 1;
+            float in[CONV_VX + 2];
+            const bool row_ok = dd >= 0 && dd < D && hh >= 0 && hh < H;
+            const float *row = frame + ((size_t)(z0 + (row_ok ? dd : 0)) * Y + (y0 + (row_ok ? hh : 0))) * X + x0;
+#pragma unroll
+            for (int i = 0; i < CONV_VX + 2; ++i) {
+                const int ww = w + i - 1;
+                in[i] = (row_ok && ww >= 0 && ww < W) ? __ldg(row + ww) : 0.0f;
+            }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 *wv = reinterpret_cast<const float4 *>(w_s + (zy * 3 + dx) * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 k4 = wv[q];
+#pragma unroll
+                    for (int j = 0; j < CONV_VX; ++j) {
+                        acc[j][q * 4 + 0] = fmaf(in[j + dx], k4.x, acc[j][q * 4 + 0]);
+                        acc[j][q * 4 + 1] = fmaf(in[j + dx], k4.y, acc[j][q * 4 + 1]);
+                        acc[j][q * 4 + 2] = fmaf(in[j + dx], k4.z, acc[j][q * 4 + 2]);
+                        acc[j][q * 4 + 3] = fmaf(in[j + dx], k4.w, acc[j][q * 4 + 3]);
+                    }
+                }
+            }
         }
-        __half *o = raw + ((size_t)n * vox + v) * 32;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float f[8];
+        for (int j = 0; j < CONV_VX; ++j) {
+            if (w + j >= W) break;
+            __half *o = raw + ((size_t)n * vox + ((size_t)d * H + h) * W + w + j) * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = acc[q * 8 + j];
-            store8h(o + q * 8, f);
-        }
+            for (int q = 0; q < 4; ++q) {
+                float f[8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            ssum[c] += acc[c];
-            ssq[c] = fmaf(acc[c], acc[c], ssq[c]);
+                for (int e = 0; e < 8; ++e) f[e] = acc[j][q * 8 + e];
+                store8h(o + q * 8, f);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                ssum[c] += acc[j][c];
+                ssq[c] = fmaf(acc[j][c], acc[j][c], ssq[c]);
+            }
         }
     }
     block_reduce_atomic<32>(ssum, stats + (size_t)n * 32 * 2 + 0, 2);
@@ -279,34 +309,63 @@ conv_out_kernel(const float *__restrict__ raw8, const unsigned long long *__rest
 #pragma unroll
     for (int c = 0; c < 5; ++c) ssum[c] = ssq[c] = 0.0f;
     const float *src = raw8 + (size_t)n * vox * 8;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vox;
-         v += (size_t)gridDim.x * blockDim.x) {
-        const int w = (int)(v % W);
-        const size_t t = v / W;
-        const int h = (int)(t % H);
-        const int d = (int)(t / H);
-        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    // a thread computes CONV_VX voxels stacked along y (x stays the fastest index across threads,
+    // so every load and store is coalesced): an input position feeds up to 3 of them, a weight
+    // read from shared memory feeds all of them
+    const int hq = (H + CONV_VX - 1) / CONV_VX;
+    const size_t units = (size_t)D * hq * W;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units;
+         u += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(u % W);
+        const size_t t = u / W;
+        const int h = (int)(t % hq) * CONV_VX;
+        const int d = (int)(t / hq);
+        float acc[CONV_VX][5];
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-            const int dd = d + tap / 9 - 1, hh = h + (tap / 3) % 3 - 1, ww = w + tap % 3 - 1;
-            if (dd < 0 || dd >= D || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            const float4 *p = reinterpret_cast<const float4 *>(src + (((size_t)dd * H + hh) * W + ww) * 8);
-            const float4 lo = __ldg(p), hi = __ldg(p + 1);
-            const float a[5] = {fmaxf(fmaf(lo.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(lo.y, sc[1], sh[1]), 0.f),
-                                fmaxf(fmaf(lo.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(lo.w, sc[3], sh[3]), 0.f),
-                                fmaxf(fmaf(hi.x, sc[4], sh[4]), 0.f)};
+        for (int j = 0; j < CONV_VX; ++j)
 #pragma unroll
-            for (int ci = 0; ci < 5; ++ci)
+            for (int c = 0; c < 5; ++c) acc[j][c] = 0.f;
 #pragma unroll
-                for (int co = 0; co < 5; ++co) acc[co] = fmaf(a[ci], w_s[tap * 25 + ci * 5 + co], acc[co]);
+        for (int dz = 0; dz < 3; ++dz) {
+            const int dd = d + dz - 1;
+            if (dd < 0 || dd >= D) continue;
+#pragma unroll
+            for (int r = 0; r < CONV_VX + 2; ++r) {
+                const int hh = h + r - 1;
+                if (hh < 0 || hh >= H) continue;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int ww = w + dx - 1;
+                    if (ww < 0 || ww >= W) continue;
+                    const float4 *p = reinterpret_cast<const float4 *>(src + (((size_t)dd * H + hh) * W + ww) * 8);
+                    const float4 lo = __ldg(p), hi = __ldg(p + 1);
+                    const float a[5] = {fmaxf(fmaf(lo.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(lo.y, sc[1], sh[1]), 0.f),
+                                        fmaxf(fmaf(lo.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(lo.w, sc[3], sh[3]), 0.f),
+                                        fmaxf(fmaf(hi.x, sc[4], sh[4]), 0.f)};
+#pragma unroll
+                    for (int j = 0; j < CONV_VX; ++j) {
+                        const int dy = r - j;                   // this row is tap dy of output row h + j
+                        if (dy < 0 || dy > 2) continue;
+                        const float *k = w_s + ((dz * 3 + dy) * 3 + dx) * 25;
+#pragma unroll
+                        for (int ci = 0; ci < 5; ++ci)
+#pragma unroll
+                            for (int co = 0; co < 5; ++co) acc[j][co] = fmaf(a[ci], k[ci * 5 + co], acc[j][co]);
+                    }
+                }
+            }
         }
-        float4 *o = reinterpret_cast<float4 *>(raw9 + ((size_t)n * vox + v) * 8);
-        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        o[1] = make_float4(acc[4], 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            ssum[c] += acc[c];
-            ssq[c] = fmaf(acc[c], acc[c], ssq[c]);
+        for (int j = 0; j < CONV_VX; ++j) {
+            if (h + j >= H) break;
+            float4 *o = reinterpret_cast<float4 *>(raw9 + ((size_t)n * vox + ((size_t)d * H + h + j) * W + w) * 8);
+            o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            o[1] = make_float4(acc[j][4], 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                ssum[c] += acc[j][c];
+                ssq[c] = fmaf(acc[j][c], acc[j][c], ssq[c]);
+            }
         }
     }
     block_reduce_atomic<5>(ssum, stats9 + (size_t)n * 5 * 2 + 0, 2);

@@ -6,14 +6,15 @@
 #include "../../iterseg_b200/csrc/sm100.cuh"
 using namespace isg::sm100;
 
-__global__ void __launch_bounds__(128, 1) k(long long *out, int N, int rb, int shift_rows, int nmma, int nacc, int sameab) {
+__global__ void __launch_bounds__(128, 1) k(long long *out, int N, int rb, int shift_rows, int nmma, int nacc, int mode) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t raw = smem_u32(smem_dyn);
     uint8_t *base = smem_dyn + (((raw + 1023u) & ~1023u) - raw);
     __shared__ uint64_t bar;
+    __shared__ uint64_t bar2[4];
     __shared__ uint32_t tslot;
     for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(base)[i] = 0x3c003c00u;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&bar2[i], 1); fence_barrier_init(); }
     if (threadIdx.x < 32) { tmem_alloc(&tslot, 512); tmem_relinquish(); }
     fence_proxy_async();
     tc_fence_before();
@@ -39,6 +40,9 @@ __global__ void __launch_bounds__(128, 1) k(long long *out, int N, int rb, int s
                 const uint64_t bd = ((uint64_t)hi << 32) | (b0 + ksel);
                 umma_f16(tmem + (j & 1) * acc1, ad, bd, idesc, 1u);
             }
+            if (mode & 1) { umma_commit(&bar2[0]); umma_commit(&bar2[1]); }       // two commits per 18 MMAs
+            if (mode & 2) { mbar_wait(&bar2[2], 1u); tc_fence_after(); }          // a wait that passes at once
+            if (mode & 4) { mbar_wait(&bar2[0], (uint32_t)(i / 18) & 1u); tc_fence_after(); }   // wait for this tile's commit
         }
         umma_commit(&bar);
         long long t1 = clock64();
@@ -59,12 +63,14 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int nmma = 4608;
     printf("%5s %4s %6s %5s | %10s %10s\n", "N", "rb", "shift", "nacc", "issue clk", "done clk/MMA");
-    for (int rb : {128, 64})
-        for (int N : {16, 32, 64, 128, 256})
-            for (int shift : {0, 1, 8})
-                for (int nacc : {1, 2}) {
-                    if (nacc * N > 512) continue;
-                    k<<<1, 128, smem>>>(d, N, rb, shift, nmma, nacc, 0);
+    for (int rb : {64})
+        for (int N : {32, 48, 96, 192})
+            for (int shift : {1})
+                for (int nacc : {1, 2, 10, 11, 12, 13}) {
+                    const int mode = nacc >= 10 ? nacc - 9 : 0;     // 10: commits, 11: free wait, 12: both, 13: dependent wait
+                    const int na = nacc >= 10 ? 2 : nacc;
+                    if (na * N > 512) continue;
+                    k<<<1, 128, smem>>>(d, N, rb, shift, nmma, na, mode == 4 ? 5 : mode);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
