@@ -87,8 +87,21 @@ int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, int aff_origi
  *   labels           (Z+2, Y+2, X+2) uint32, must be zero on entry; written in place
  *   mask_out         (Z+2, Y+2, X+2) uint8: the kept mask (third return value)
  *   seeds_out        capacity max_seeds flat PADDED indices of the kept seeds, label order
- *   counts_out       device int64[4]: {n_seeds_kept, n_candidates, n_components, n_multi_seed_components}
+ *   counts_out       device int64[8]: {n_seeds_kept, n_candidates, n_components,
+ *                    n_multi_seed_components, halo_violation, 0, 0, 0}
  *   otsu_out         device float[1]: the threshold used
+ *
+ * Slab mode (one z-slab of a larger volume, extended by halo planes):
+ *   use_aff_div / aff_div   per-channel affinity maxima of the WHOLE volume (an all-reduce of
+ *                           isg_slab_stats stage 0) instead of the local maxima (watershed.py:195)
+ *   own_z0, own_z1          the planes [own_z0, own_z1) of this volume that the caller will keep
+ *                           (own_z1 == 0: everything)
+ *   open_faces              bit 0: the volume continues below plane 0, bit 1: above plane z-1.
+ *                           A mask component that touches an open face AND the own planes cannot
+ *                           be segmented exactly from this slab: counts_out[4] is set to 1
+ *   seed_keys_out           optional device uint64[max_seeds]: for every kept seed (label order)
+ *                           (~order_preserving_bits(smoothed centre value) << 32) | flat UNPADDED
+ *                           voxel index -- the key the seeds are sorted by, for a global relabel
  */
 typedef struct {
     int aff_ch[3];
@@ -102,6 +115,12 @@ typedef struct {
     int64_t min_area;
     int64_t max_area;
     float scale[3]; /* |scale| multiplies the affinities (watershed.py:23-24); 1,1,1 = None */
+    int use_aff_div;
+    float aff_div[3];
+    int own_z0;
+    int own_z1;
+    int open_faces;
+    unsigned long long *seed_keys_out;
 } isg_post_params;
 
 size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds);
@@ -111,6 +130,32 @@ int isg_segment_features(const float *feats, int n_chan, int64_t z, int64_t y, i
                          uint32_t *labels, uint8_t *mask_out, int64_t *seeds_out,
                          int64_t max_seeds, int64_t *counts_out, float *otsu_out,
                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- spatial (z-slab) sharding of one large volume: global statistics -----
+ * The scalars of segment_output_image that couple the whole volume, computed slab by slab so
+ * that they can be combined with an all-reduce (MAX / MIN / SUM) and fed back through
+ * isg_post_params (aff_div, absolute_thresh):
+ *   stage 0: chan_max_out[3] = maxima of the affinity channels over the own planes
+ *            (watershed.py:195); minmax_io[2] = min / max of the sigma=2 smoothed mask channel
+ *            over the own planes (the smoothing sees the halo planes of the slab)
+ *   stage 1: hist_out[256] = numpy.histogram(smoothed own planes, 256, range = minmax_io)
+ *            with minmax_io holding the GLOBAL min / max
+ * isg_otsu_from_hist: threshold_otsu on the (summed) histogram, numpy float32 arithmetic.
+ * All outputs are device pointers; feats is the (C, z, y, x) slab INCLUDING its halo planes. */
+int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
+                   const isg_post_params *params, const double *gauss2_host, int stage,
+                   float *minmax_io, float *chan_max_out, unsigned long long *hist_out,
+                   void *workspace, size_t workspace_bytes, void *stream);
+int isg_otsu_from_hist(const unsigned long long *hist, const float *minmax, float *thr_out,
+                       void *stream);
+/* keys[0..n) ascending, in place (tmp: n uint64 of scratch + isg_sort_tmp_bytes(n) bytes) */
+size_t isg_sort_tmp_bytes(int64_t n);
+int isg_sort_keys_u64(unsigned long long *keys, int64_t n, void *tmp, size_t tmp_bytes, void *stream);
+/* labels[i] (non-zero, <= n_local) -> 1 + position of local_keys[labels[i]-1] in the sorted
+ * global key list (a label whose key is missing becomes 0 and *missing_out is set to 1) */
+int isg_relabel_by_keys(uint32_t *labels, int64_t n, const unsigned long long *local_keys,
+                        int64_t n_local, const unsigned long long *global_sorted_keys,
+                        int64_t n_global, uint32_t *lut_scratch, int *missing_out, void *stream);
 
 /* ---- 3-D U-Net over chunks ----------------------------------------------
  * Replaces process_chunks + predict_chunk_feature_map + UNet.forward

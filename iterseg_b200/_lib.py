@@ -17,7 +17,8 @@ class PostParams(_c.Structure):
     _fields_ = [('aff_ch', _i32 * 3), ('mask_ch', _i32), ('cent_ch', _i32), ('r1', _i32),
                 ('r2', _i32), ('peak_thresh', _f32), ('use_absolute_thresh', _i32),
                 ('absolute_thresh', _f32), ('min_area', _i64), ('max_area', _i64),
-                ('scale', _f32 * 3)]
+                ('scale', _f32 * 3), ('use_aff_div', _i32), ('aff_div', _f32 * 3), ('own_z0', _i32),
+                ('own_z1', _i32), ('open_faces', _i32), ('seed_keys_out', _vp)]
 
 
 # name -> (restype, argtypes); this table is also what the symbol-export test checks
@@ -32,6 +33,12 @@ SIGNATURES = {
     'isg_post_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
     'isg_segment_features': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _vp,
                                     _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    'isg_slab_stats': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _i32, _vp, _vp, _vp,
+                              _vp, _sz, _vp]),
+    'isg_otsu_from_hist': (_i32, [_vp, _vp, _vp, _vp]),
+    'isg_sort_tmp_bytes': (_sz, [_i64]),
+    'isg_sort_keys_u64': (_i32, [_vp, _i64, _vp, _sz, _vp]),
+    'isg_relabel_by_keys': (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     'isg_unet_packed_weight_bytes': (_sz, []),
     'isg_unet_weights_pack': (_i32, [_vp, _i32, _vp, _vp]),
     'isg_unet_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32]),

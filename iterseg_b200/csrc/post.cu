@@ -28,7 +28,8 @@ struct GaussW {
 template <int AXIS>
 __global__ void __launch_bounds__(256)
 gauss_axis_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t Z, uint32_t Y,
-                  uint32_t X, GaussW gw, uint32_t *minmax /* nullable: ordered min, max */) {
+                  uint32_t X, GaussW gw, uint32_t *minmax /* nullable: ordered min, max */,
+                  uint32_t mm_z0 = 0, uint32_t mm_z1 = 0xFFFFFFFFu /* planes that count for min/max */) {
     const uint64_t n = (uint64_t)Z * Y * X;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint32_t len = AXIS == 0 ? Z : (AXIS == 1 ? Y : X);
@@ -50,7 +51,7 @@ gauss_axis_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_
         }
         float o = (float)acc;
         out[v] = o;
-        if (minmax) {
+        if (minmax && z >= mm_z0 && z < mm_z1) {
             uint32_t k = f32_ord(o);
             lo = min(lo, k);
             hi = max(hi, k);
@@ -68,10 +69,10 @@ gauss_axis_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_
 
 // per-channel maximum of up to 3 planes (np.max(affinities, axis=(1,2,3)), watershed.py:195)
 __global__ void __launch_bounds__(256)
-chan_max_kernel(const float *__restrict__ feats, uint64_t n, int c0, int c1, int c2,
+chan_max_kernel(const float *__restrict__ feats, uint64_t chan_stride, uint64_t n, int c0, int c1, int c2,
                 uint32_t *__restrict__ out_ord) {
     const int ch = blockIdx.y == 0 ? c0 : (blockIdx.y == 1 ? c1 : c2);
-    const float *base = feats + (uint64_t)ch * n;
+    const float *base = feats + (uint64_t)ch * chan_stride;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     float m = -INFINITY;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
@@ -244,7 +245,8 @@ seed_filter_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n_cand,
                    const uint32_t *__restrict__ nontrivial, const uint32_t *__restrict__ parent,
                    const uint32_t *__restrict__ comp_size, uint64_t min_area, uint64_t max_area,
                    uint32_t Z, uint32_t Y, uint32_t X, int64_t *__restrict__ seeds_out,
-                   uint32_t cap, uint32_t *__restrict__ labels, uint32_t *__restrict__ n_kept_out) {
+                   uint32_t cap, uint32_t *__restrict__ labels, uint32_t *__restrict__ n_kept_out,
+                   unsigned long long *__restrict__ keys_out /* nullable */) {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ uint32_t carry;
@@ -277,6 +279,7 @@ seed_filter_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n_cand,
             if (k < cap) {
                 seeds_out[k] = (int64_t)p;
                 labels[p] = k + 1;
+                if (keys_out) keys_out[k] = cand_sorted[i];
             }
         }
         __syncthreads();
@@ -306,12 +309,42 @@ mask_keep_kernel(const uint8_t *__restrict__ mask0, const uint32_t *__restrict__
     if ((threadIdx.x & 31) == 0 && roots) atomicAdd(n_components, roots);
 }
 
+// Slab mode: components that touch an open z face of the slab are only partially known.
+__global__ void __launch_bounds__(256)
+slab_face_kernel(const uint32_t *__restrict__ parent, uint32_t *__restrict__ flag, uint32_t Zp,
+                 uint32_t Yp, uint32_t Xp, int open_faces) {
+    const uint64_t plane = (uint64_t)Yp * Xp;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * plane; i += stride) {
+        const int face = i >= plane;
+        if (!((open_faces >> face) & 1)) continue;
+        const uint64_t v = (face ? (uint64_t)(Zp - 2) : 1ull) * plane + (i - face * plane);
+        const uint32_t r = parent[v];
+        if (r != CCL_NONE) flag[r] = 1u;
+    }
+}
+__global__ void __launch_bounds__(256)
+slab_guard_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ flag, uint32_t Yp,
+                  uint32_t Xp, uint32_t own_z0, uint32_t own_z1, uint32_t *__restrict__ violation) {
+    const uint64_t plane = (uint64_t)Yp * Xp;
+    const uint64_t v0 = (uint64_t)(own_z0 + 1) * plane, v1 = (uint64_t)(own_z1 + 1) * plane;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += stride) {
+        const uint32_t r = parent[v];
+        if (r != CCL_NONE && flag[r]) bad = true;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(violation, 1u);
+}
+
 __global__ void counts_kernel(const uint32_t *n_kept, const uint32_t *n_cand, const uint32_t *n_components,
-                              const uint32_t *n_multi, int64_t *out) {
+                              const uint32_t *n_multi, const uint32_t *violation, int64_t *out) {
     out[0] = *n_kept;
     out[1] = *n_cand;
     out[2] = *n_components;
     out[3] = *n_multi;
+    out[4] = *violation;
+    out[5] = out[6] = out[7] = 0;
 }
 
 struct PostBuffers {
@@ -319,7 +352,7 @@ struct PostBuffers {
     uint64_t *cand_a, *cand_b;
     unsigned char *cub_tmp;
     size_t cub_bytes;
-    uint32_t *scal;        // 0,1: minmax ord; 2: n_cand; 3: nontrivial; 4: n_kept; 5: n_components; 8..10: aff max ord
+    uint32_t *scal;        // 0,1: minmax ord; 2: n_cand; 3: nontrivial; 4: n_kept; 5: n_components; 6: halo violation; 8..10: aff max ord
     float *fscal;          // 0..2: aff max; 3: otsu thr
     float *edges;
     unsigned long long *hist;
@@ -405,11 +438,15 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
         ISG_CUDA(cudaMemcpyAsync(b.scal, &init, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     }
     // ---- affinity channel maxima -------------------------------------------------
-    chan_max_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(feats, n, prm->aff_ch[0], prm->aff_ch[1],
-                                                     prm->aff_ch[2], b.scal + 8);
-    ISG_LAUNCHED();
-    ord_to_float_kernel<<<1, 32, 0, st>>>(b.scal + 8, b.fscal, 3);
-    ISG_LAUNCHED();
+    if (prm->use_aff_div) {
+        ISG_CUDA(cudaMemcpyAsync(b.fscal, prm->aff_div, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        chan_max_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(feats, n, n, prm->aff_ch[0], prm->aff_ch[1],
+                                                         prm->aff_ch[2], b.scal + 8);
+        ISG_LAUNCHED();
+        ord_to_float_kernel<<<1, 32, 0, st>>>(b.scal + 8, b.fscal, 3);
+        ISG_LAUNCHED();
+    }
     // ---- seeds --------------------------------------------------------------------
     const float *cent = feats + (uint64_t)prm->cent_ch * n;
     const float *smoothed_c = cent;
@@ -482,8 +519,20 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     ISG_LAUNCHED();
     seed_filter_kernel<<<1, 1024, 0, st>>>(cand_sorted, n_cand, b.scal + 3, b.parent, b.comp_size,
                                            (uint64_t)prm->min_area, (uint64_t)prm->max_area, Z, Y, X,
-                                           seeds_out, (uint32_t)max_seeds, labels, b.scal + 4);
+                                           seeds_out, (uint32_t)max_seeds, labels, b.scal + 4,
+                                           prm->seed_keys_out);
     ISG_LAUNCHED();
+    if (prm->open_faces) {
+        // slab mode: is every component that reaches the own planes completely inside the slab?
+        const uint32_t oz0 = (uint32_t)prm->own_z0, oz1 = prm->own_z1 > 0 ? (uint32_t)prm->own_z1 : Z;
+        ISG_REQUIRE(oz0 < oz1 && oz1 <= Z, ISG_ERR_ARG, "bad own plane range");
+        uint32_t *flag = b.flood.lidmap;          // scratch until the flood stage writes it
+        ISG_CUDA(cudaMemsetAsync(flag, 0, np * sizeof(uint32_t), st));
+        slab_face_kernel<<<grid, 256, 0, st>>>(b.parent, flag, Z + 2, Y + 2, X + 2, prm->open_faces);
+        ISG_LAUNCHED();
+        slab_guard_kernel<<<grid, 256, 0, st>>>(b.parent, flag, Y + 2, X + 2, oz0, oz1, b.scal + 6);
+        ISG_LAUNCHED();
+    }
     // ---- flood ----------------------------------------------------------------------
     FloodGeom g;
     g.aff = feats + (uint64_t)c0 * n;
@@ -500,8 +549,183 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     int rc = flood_stage_run(b.flood, g, mask_out, b.parent, b.comp_size, b.comp_label, seeds_out,
                              (int64_t)n_cand, b.scal + 4, labels, st);
     if (rc != ISG_OK) return rc;
-    counts_kernel<<<1, 1, 0, st>>>(b.scal + 4, b.scal + 2, b.scal + 5, b.flood.scalars + 1, counts_out);
+    counts_kernel<<<1, 1, 0, st>>>(b.scal + 4, b.scal + 2, b.scal + 5, b.flood.scalars + 1, b.scal + 6,
+                                   counts_out);
     ISG_LAUNCHED();
     ISG_CUDA(cudaMemcpyAsync(otsu_out, b.fscal + 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return ISG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// slab mode: volume-wide statistics, slab by slab
+// ---------------------------------------------------------------------------
+namespace isg {
+__global__ void float_to_ord_kernel(const float *__restrict__ in, uint32_t *__restrict__ out, int n) {
+    int i = threadIdx.x;
+    if (i < n) out[i] = f32_ord(in[i]);
+}
+__global__ void __launch_bounds__(256)
+lut_kernel(const unsigned long long *__restrict__ local_keys, int64_t n_local,
+           const unsigned long long *__restrict__ sorted, int64_t n_global, uint32_t *__restrict__ lut,
+           int *__restrict__ missing) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    const unsigned long long k = local_keys[i];
+    int64_t lo = 0, hi = n_global;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_global && sorted[lo] == k) lut[i] = (uint32_t)(lo + 1);
+    else { lut[i] = 0u; *missing = 1; }
+}
+__global__ void __launch_bounds__(256)
+relabel_kernel(uint32_t *__restrict__ labels, int64_t n, const uint32_t *__restrict__ lut, int64_t n_local,
+               int *__restrict__ missing) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t l = labels[i];
+        if (l == 0) continue;
+        if ((int64_t)l > n_local) { labels[i] = 0; *missing = 1; continue; }
+        labels[i] = lut[l - 1];
+    }
+}
+}  // namespace isg
+
+extern "C" int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
+                              const isg_post_params *prm, const double *gauss2_host, int stage,
+                              float *minmax_io, float *chan_max_out, unsigned long long *hist_out,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    ISG_REQUIRE(feats && prm && minmax_io, ISG_ERR_ARG, "isg_slab_stats: null pointer");
+    ISG_REQUIRE(z >= 1 && y >= 1 && x >= 1 && prm->r2 >= 0 && prm->r2 <= 11, ISG_ERR_ARG, "bad extents");
+    ISG_REQUIRE(stage == 0 || stage == 1, ISG_ERR_ARG, "stage must be 0 or 1");
+    ISG_REQUIRE(prm->mask_ch >= 0 && prm->mask_ch < n_chan, ISG_ERR_ARG, "bad channel index");
+    const uint64_t n = (uint64_t)z * y * x;
+    const uint32_t Z = (uint32_t)z, Y = (uint32_t)y, X = (uint32_t)x;
+    const uint32_t oz0 = (uint32_t)prm->own_z0, oz1 = prm->own_z1 > 0 ? (uint32_t)prm->own_z1 : Z;
+    ISG_REQUIRE(oz0 < oz1 && oz1 <= Z, ISG_ERR_ARG, "bad own plane range");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(workspace, workspace_bytes);
+    float *tmp_a = cv.take<float>(n), *tmp_b = cv.take<float>(n);
+    uint32_t *scal = cv.take<uint32_t>(64);
+    float *edges = cv.take<float>(320);
+    ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE, "isg_slab_stats: workspace too small (%zu < %zu)",
+                workspace_bytes, cv.off);
+    const int sms = num_sms();
+    const int grid = sms * 8;
+    GaussW g2;
+    g2.r = prm->r2;
+    for (int i = 0; i <= prm->r2; ++i) g2.w[i] = gauss2_host[i];
+    const uint64_t plane = (uint64_t)Y * X;
+    const float *mraw = feats + (uint64_t)prm->mask_ch * n;
+    ISG_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(uint32_t), st));
+    {
+        const uint32_t init = 0xFFFFFFFFu;
+        ISG_CUDA(cudaMemcpyAsync(scal, &init, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    uint32_t *mm = stage == 0 ? scal : nullptr;
+    const float *s = tmp_a;
+    if (prm->r2 > 0) {
+        gauss_axis_kernel<0><<<grid, 256, 0, st>>>(mraw, tmp_a, Z, Y, X, g2, nullptr);
+        ISG_LAUNCHED();
+        gauss_axis_kernel<1><<<grid, 256, 0, st>>>(tmp_a, tmp_b, Z, Y, X, g2, nullptr);
+        ISG_LAUNCHED();
+        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(tmp_b, tmp_a, Z, Y, X, g2, mm, oz0, oz1);
+        ISG_LAUNCHED();
+    } else {
+        GaussW id;
+        id.r = 0;
+        id.w[0] = 1.0;
+        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(mraw, tmp_a, Z, Y, X, id, mm, oz0, oz1);
+        ISG_LAUNCHED();
+    }
+    if (stage == 0) {
+        ISG_REQUIRE(chan_max_out, ISG_ERR_ARG, "isg_slab_stats: chan_max_out is NULL");
+        for (int i = 0; i < 3; ++i)
+            ISG_REQUIRE(prm->aff_ch[i] >= 0 && prm->aff_ch[i] < n_chan, ISG_ERR_ARG, "bad affinity channel");
+        ord_to_float_kernel<<<1, 32, 0, st>>>(scal, minmax_io, 2);
+        ISG_LAUNCHED();
+        chan_max_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(feats + oz0 * plane, n, (uint64_t)(oz1 - oz0) * plane,
+                                                         prm->aff_ch[0], prm->aff_ch[1], prm->aff_ch[2],
+                                                         scal + 8);
+        ISG_LAUNCHED();
+        ord_to_float_kernel<<<1, 32, 0, st>>>(scal + 8, chan_max_out, 3);
+        ISG_LAUNCHED();
+        return ISG_OK;
+    }
+    ISG_REQUIRE(hist_out, ISG_ERR_ARG, "isg_slab_stats: hist_out is NULL");
+    float_to_ord_kernel<<<1, 32, 0, st>>>(minmax_io, scal, 2);
+    ISG_LAUNCHED();
+    ISG_CUDA(cudaMemsetAsync(hist_out, 0, 256 * sizeof(unsigned long long), st));
+    hist_edges_kernel<<<1, 288, 0, st>>>(scal, edges);
+    ISG_LAUNCHED();
+    hist_kernel<<<sms * 4, 256, 0, st>>>(s + oz0 * plane, (uint64_t)(oz1 - oz0) * plane, scal, edges, hist_out);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+extern "C" int isg_otsu_from_hist(const unsigned long long *hist, const float *minmax, float *thr_out,
+                                  void *stream) {
+    ISG_REQUIRE(hist && minmax && thr_out, ISG_ERR_ARG, "isg_otsu_from_hist: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: ordered min/max + the 257 float32 bin edges live behind thr_out's caller? no: static per device
+    static thread_local uint32_t *scal = nullptr;
+    static thread_local float *edges = nullptr;
+    static thread_local int dev_of = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_of != dev) {
+        ISG_CUDA(cudaMalloc(&scal, 64 * sizeof(uint32_t)));
+        ISG_CUDA(cudaMalloc(&edges, 320 * sizeof(float)));
+        dev_of = dev;
+    }
+    float_to_ord_kernel<<<1, 32, 0, st>>>(minmax, scal, 2);
+    ISG_LAUNCHED();
+    hist_edges_kernel<<<1, 288, 0, st>>>(scal, edges);
+    ISG_LAUNCHED();
+    otsu_kernel<<<1, 32, 0, st>>>(hist, edges, scal, thr_out);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+extern "C" size_t isg_sort_tmp_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    size_t b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n);
+    return b + 256 + (size_t)n * sizeof(unsigned long long);
+}
+
+extern "C" int isg_sort_keys_u64(unsigned long long *keys, int64_t n, void *tmp, size_t tmp_bytes, void *stream) {
+    ISG_REQUIRE(n >= 0 && (n == 0 || (keys && tmp)), ISG_ERR_ARG, "isg_sort_keys_u64: null pointer");
+    if (n <= 1) return ISG_OK;
+    ISG_REQUIRE(tmp_bytes >= isg_sort_tmp_bytes(n), ISG_ERR_WORKSPACE, "isg_sort_keys_u64: tmp too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *alt = (unsigned long long *)tmp;
+    size_t cb = tmp_bytes - (size_t)n * sizeof(unsigned long long);
+    char *cub_tmp = (char *)tmp + (((size_t)n * sizeof(unsigned long long) + 255) & ~(size_t)255);
+    cb -= (size_t)(cub_tmp - ((char *)tmp + (size_t)n * sizeof(unsigned long long)));
+    ISG_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, keys, alt, (int)n, 0, 64, st));
+    count_launch(4);
+    ISG_CUDA(cudaMemcpyAsync(keys, alt, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    return ISG_OK;
+}
+
+extern "C" int isg_relabel_by_keys(uint32_t *labels, int64_t n, const unsigned long long *local_keys,
+                                   int64_t n_local, const unsigned long long *global_sorted_keys,
+                                   int64_t n_global, uint32_t *lut_scratch, int *missing_out, void *stream) {
+    ISG_REQUIRE(labels && missing_out && n >= 0 && n_local >= 0 && n_global >= 0, ISG_ERR_ARG,
+                "isg_relabel_by_keys: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    ISG_CUDA(cudaMemsetAsync(missing_out, 0, sizeof(int), st));
+    if (n_local > 0) {
+        ISG_REQUIRE(local_keys && global_sorted_keys && lut_scratch, ISG_ERR_ARG, "isg_relabel_by_keys: null pointer");
+        lut_kernel<<<(int)((n_local + 255) / 256), 256, 0, st>>>(local_keys, n_local, global_sorted_keys, n_global,
+                                                                  lut_scratch, missing_out);
+        ISG_LAUNCHED();
+    }
+    if (n > 0) {
+        relabel_kernel<<<num_sms() * 8, 256, 0, st>>>(labels, n, lut_scratch, n_local, missing_out);
+        ISG_LAUNCHED();
+    }
     return ISG_OK;
 }

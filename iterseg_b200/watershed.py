@@ -52,24 +52,10 @@ def _as_device(a, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
 
 
-def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centroids_channel=4,
-                            thresholding_channel=3, scale=None, absolute_thresh=None,
-                            max_seeds=None, min_area=10, max_area=10000000):
-    """Device-resident core of segment_output_image.
-
-    feats  : (C,Z,Y,X) float32 CUDA tensor (not modified)
-    labels : (Z+2,Y+2,X+2) uint32-as-int32 CUDA tensor, all zero; written in place
-    Returns (seeds_padded_flat int64[max], counts int64[4], mask uint8 padded, otsu float[1]),
-    all CUDA tensors; counts = (n_seeds, n_candidates, n_components, n_multi_seed_components).
-    """
-    lib = _lib.load()
-    assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
-    assert labels.is_cuda and labels.dtype == torch.int32 and labels.is_contiguous()
-    C, Z, Y, X = feats.shape
-    assert tuple(labels.shape) == (Z + 2, Y + 2, X + 2)
-    dev = feats.device
-    if max_seeds is None:
-        max_seeds = max(1 << 16, (Z * Y * X) // 8)
+def post_params(affinities_channels=(0, 1, 2), centroids_channel=4, thresholding_channel=3,
+                scale=None, absolute_thresh=None, min_area=10, max_area=10000000):
+    """(isg_post_params, sigma=1 half kernel, sigma=2 half kernel) with the reference's constants
+    (watershed.py:227,234-235,241-246)."""
     p = _lib.PostParams()
     for i, c in enumerate(affinities_channels):
         p.aff_ch[i] = int(c)
@@ -86,11 +72,45 @@ def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centro
         np.broadcast_to(np.asarray(scale, np.float32).reshape(-1), (3,)))
     for i in range(3):
         p.scale[i] = float(sc[i])
+    return p, w1, w2
+
+
+def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centroids_channel=4,
+                            thresholding_channel=3, scale=None, absolute_thresh=None,
+                            max_seeds=None, min_area=10, max_area=10000000, slab=None):
+    """Device-resident core of segment_output_image.
+
+    feats  : (C,Z,Y,X) float32 CUDA tensor (not modified)
+    labels : (Z+2,Y+2,X+2) uint32-as-int32 CUDA tensor, all zero; written in place
+    Returns (seeds_padded_flat int64[max], counts int64[8], mask uint8 padded, otsu float[1]),
+    all CUDA tensors; counts = (n_seeds, n_candidates, n_components, n_multi_seed_components,
+    halo_violation, 0, 0, 0).
+    slab: None, or a dict for one z-slab of a larger volume (iterseg_b200/slab.py):
+    aff_div (3 floats), own_z0, own_z1, open_faces, seed_keys (int64 CUDA tensor [max_seeds]).
+    """
+    lib = _lib.load()
+    assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
+    assert labels.is_cuda and labels.dtype == torch.int32 and labels.is_contiguous()
+    C, Z, Y, X = feats.shape
+    assert tuple(labels.shape) == (Z + 2, Y + 2, X + 2)
+    dev = feats.device
+    if max_seeds is None:
+        max_seeds = max(1 << 16, (Z * Y * X) // 8)
+    p, w1, w2 = post_params(affinities_channels, centroids_channel, thresholding_channel, scale,
+                            absolute_thresh, min_area, max_area)
+    if slab is not None:
+        p.use_aff_div = 1
+        for i in range(3):
+            p.aff_div[i] = float(slab['aff_div'][i])
+        p.own_z0, p.own_z1, p.open_faces = int(slab['own_z0']), int(slab['own_z1']), int(slab['open_faces'])
+        keys = slab['seed_keys']
+        assert keys.is_cuda and keys.dtype == torch.int64 and keys.numel() >= max_seeds
+        p.seed_keys_out = keys.data_ptr()
     nbytes = lib.isg_post_workspace_bytes(Z, Y, X, max_seeds)
     ws = _workspace('post', (Z, Y, X, max_seeds), nbytes, dev)
     mask = torch.empty((Z + 2, Y + 2, X + 2), dtype=torch.uint8, device=dev)
     seeds = torch.empty(max_seeds, dtype=torch.int64, device=dev)
-    counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    counts = torch.zeros(8, dtype=torch.int64, device=dev)
     otsu = torch.zeros(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.isg_segment_features(

@@ -147,3 +147,27 @@ def test_label_count_allgather_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
+
+
+def test_plan_slabs_partitions_chunks_exactly_once():
+    """Slab borders coincide with chunk-interior borders; every chunk of the GLOBAL list belongs to
+    exactly one rank (its BatchNorm batch is never split or recomputed)."""
+    from iterseg_b200 import slab
+    for shape, world in (((256, 2048, 2048), 8), ((33, 512, 512), 2), ((96, 160, 160), 4)):
+        slabs, (st, lo, hi) = slab.plan_slabs(shape, (10, 256, 256) if shape[1] >= 256 else (10, 64, 64),
+                                              (1, 64, 64) if shape[1] >= 256 else (1, 16, 16), world)
+        assert slabs[0].z0 == 0 and slabs[-1].z1 == shape[0]
+        seen = np.zeros(len(st), int)
+        for a, b in zip(slabs[:-1], slabs[1:]):
+            assert a.z1 == b.z0
+        for s in slabs:
+            seen[s.chunks] += 1
+            za, zb = st[s.chunks, 0] + lo[s.chunks, 0], st[s.chunks, 0] + hi[s.chunks, 0]
+            assert za.min() == s.z0 and zb.max() == s.z1
+            assert s.in0 <= s.z0 and s.in1 >= s.z1
+        assert (seen == 1).all()
+    slabs, _ = slab.plan_slabs((256, 2048, 2048), (10, 256, 256), (1, 64, 64), 8)
+    sizes = [s.z1 - s.z0 for s in slabs]
+    assert max(sizes) - min(sizes) <= 8 and len(slabs[0].chunks) * 8 >= 7200 * 0.9
+    with pytest.raises(ValueError):
+        slab.plan_slabs((33, 512, 512), (10, 256, 256), (1, 64, 64), 8)
