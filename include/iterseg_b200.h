@@ -40,6 +40,9 @@ const char *isg_last_error(void);
 int isg_device_check(void);
 /* how many kernels this library has launched since load (bench `gpu_launches`) */
 uint64_t isg_launch_count(void);
+/* Frame pipelining (iterseg_b200/pipeline.py): reserve n_sms SMs for the post stage of one frame
+ * while the U-Net of the next frame runs on another stream (0 = off, the default). */
+int isg_set_post_sm_reservation(int n_sms);
 
 /* ---- affinity flood ------------------------------------------------------
  * Replaces raveled_affinity_watershed (watershed.py:95-159) together with the

@@ -17,11 +17,18 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static std::atomic<int> g_post_sms{0};
+int post_sms() { return g_post_sms.load(std::memory_order_relaxed); }
 }  // namespace isg
 
 extern "C" int isg_version(void) { return 100; }
 extern "C" const char *isg_last_error(void) { return isg::g_err; }
 extern "C" uint64_t isg_launch_count(void) { return isg::g_launches.load(); }
+extern "C" int isg_set_post_sm_reservation(int n_sms) {
+    ISG_REQUIRE(n_sms >= 0 && n_sms <= isg::num_sms() / 2, ISG_ERR_ARG, "isg_set_post_sm_reservation: %d out of range", n_sms);
+    isg::g_post_sms.store(n_sms);
+    return ISG_OK;
+}
 extern "C" int isg_device_check(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

@@ -10,6 +10,10 @@ namespace isg {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// SMs set aside for the post stage while a U-Net of another frame runs beside it (0 = none):
+// the persistent conv kernels launch num_sms() - post_sms() CTAs, the shared-memory-hungry
+// flood kernels at most post_sms() SMs' worth, so neither waits for the other's CTAs to retire
+int post_sms();
 
 #define ISG_CUDA(expr)                                                                   \
     do {                                                                                 \

@@ -369,8 +369,9 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     ISG_REQUIRE(fs->ok, ISG_ERR_CUDA, "flood stage: could not create side streams");
     // upper bounds on the per-class work (the exact counts live on the device)
     const int64_t max_multi = n_seeds / 2 + 1;
+    const int flood_sms = post_sms() > 0 ? post_sms() : sms;
     auto grid_for = [&](int64_t per_sm) {
-        int64_t gsz = (int64_t)sms * per_sm;
+        int64_t gsz = (int64_t)flood_sms * per_sm;
         return (int)(gsz < max_multi ? gsz : max_multi);
     };
     ISG_CUDA(cudaEventRecord(fs->fork, st));

@@ -332,7 +332,10 @@ template <int CBLK, int G, bool FOLD>
 static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
     ISG_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<CBLK, G, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)t.smem));
-    conv3d_tc_kernel<CBLK, G, FOLD><<<t.grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
+    int grid = t.grid;
+    const int avail = num_sms() - post_sms();
+    if (grid > avail) grid = avail;
+    conv3d_tc_kernel<CBLK, G, FOLD><<<grid, CONV_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.g);
     ISG_LAUNCHED();
     return ISG_OK;
 }

@@ -112,8 +112,9 @@ def affinity_watershed_for_chunks(input_volume, current_output, chunk_size, marg
     out_is_dev = isinstance(current_output, torch.Tensor) and current_output.is_cuda
     labels = current_output.view(shape_p) if out_is_dev else \
         torch.zeros(shape_p, dtype=torch.int32, device=dev)
-    ws.segment_features_device(feats, labels, affinities_channels=(0, 1, 2),
-                               thresholding_channel=3, centroids_channel=4)
+    _, counts, _, _ = ws.segment_features_device(feats, labels, affinities_channels=(0, 1, 2),
+                                                 thresholding_channel=3, centroids_channel=4)
+    LAST_COUNTS['counts'] = counts           # device int64[8]; [0] = number of labels of this frame
     if not out_is_dev:
         direct = (isinstance(current_output, np.ndarray) and current_output.flags.c_contiguous
                   and current_output.dtype in (np.uint32, np.int32)
@@ -123,6 +124,11 @@ def affinity_watershed_for_chunks(input_volume, current_output, chunk_size, marg
         else:
             flat = current_output.reshape(-1)      # a view, like current_output.ravel() in :194
             flat[...] = labels.cpu().numpy().view(np.uint32).reshape(-1).astype(flat.dtype, copy=False)
+
+
+# (addition) device-side counters of the most recent frame, for callers that need the number of
+# labels without scanning the label volume (frame-sharded series: global label offsets)
+LAST_COUNTS = {}
 
 
 # ---------------
