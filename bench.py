@@ -48,6 +48,17 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
+def conv_traffic():
+    """DRAM bytes per conv3d_tc launch (average over the 16 layers) from the committed
+    `ncu --set full` capture of the same kernels (profiles/r01_conv_traffic.json), else None."""
+    fn = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    try:
+        with open(fn) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -277,6 +288,20 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = nvox * world / (float(t.item()) / args.steps)
 
+    # ---- post stage alone (not overlapped), device-timed: the HBM-side roofline entry -----------
+    post_ms = None
+    if rank == 0:
+        predict.predict_frame_device(net, frame, CHUNK, MARGIN, out=feats)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        reps = 3
+        p0.record()
+        for _ in range(reps):
+            labels.zero_()
+            ws.segment_features_device(feats, labels)
+        p1.record()
+        torch.cuda.synchronize()
+        post_ms = p0.elapsed_time(p1) / reps
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
@@ -303,12 +328,21 @@ def run_gpu(args, rank, local_rank, world):
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': ach_tf / peak_tf if peak_tf else None, 'traffic': None,
+                         'frac': ach_tf / peak_tf if peak_tf else None, 'traffic': conv_traffic(),
                          'kernel': 'conv3d_tc_kernel (16 launches per step)',
                          'peak_source': f'{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)',
                          'share_of_step': (tc_ms / n_fw) / ms_step if n_fw else None,
                          'unet_ms_per_step': fw_ms / n_fw if n_fw else None},
         }
+        hbm = float(peaks.get('hbm_gbs_sustained', peaks.get('hbm_gbs', 6650.0)))
+        post_bytes = 24.0 * nvox              # 5 x f32 feature reads + 1 x u32 label write per voxel
+        line['roofline_post'] = {
+            'bound': 'hbm', 'achieved': post_bytes / (post_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+            'frac': post_bytes / (post_ms * 1e-3) / 1e9 / hbm, 'traffic': None,
+            'kernel': 'post-U-Net stage (seeds, Otsu mask, components, ordered flood), timed alone',
+            'ms': post_ms,
+            'note': 'latency bound, not HBM bound: the order-exact flood of the largest multi-seed object '
+                    '(one warp, ~660 clk per voxel) sets the time; see profiles/r01_notes.md'}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             per_frame, t_unet, t_post, n_chunks = cpu_reference_step(vol_np, lab_gt, sd, 3, threads)
