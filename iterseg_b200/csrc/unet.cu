@@ -237,45 +237,51 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     // stage (a stage <= 36 KB) and as many stages as fit (>= 2).
     const bool want_fold = g.cout <= 64 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
     bool placed = false;
-    for (int cand = want_fold ? 0 : 1; cand < 2 && !placed; ++cand) {
-        const bool fold = cand == 0;
-        const int acc = fold ? 3 * g.cout : g.cout;
-        const int nsets = (!fold && g.cout >= 256) ? 1 : 2;
-        int tmax = (512 / nsets) / acc;
-        if (tmax < 1) continue;
-        if (fold) { g.P = 32; g.Ht = 4; }
-        else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
-        g.plane_rows = (g.Ht + 2) * g.P;
-        g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
-        if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
-        if (tmax > g.D) tmax = g.D;
-        for (; tmax >= 1 && !placed; --tmax) {
-            const int ngr = (g.D + tmax - 1) / tmax;
-            const int T = (g.D + ngr - 1) / ngr;
-            const long avail = budget - (long)(T + 2) * g.plane_bytes;
-            if (avail <= 0) continue;
-            if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
-                g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
-                g.b_resident = 1;
-                placed = true;
-            } else if (!fold || T >= 2) {
-                for (int G : {9, 3, 1}) {
-                    if (fold && G == 1) continue;
-                    const long sb = (long)G * tap_bytes;
-                    if (sb > 36 * 1024 && G > 1) continue;
-                    long nb = avail / sb;
-                    if (nb < 2) continue;
-                    if (nb > 6) nb = 6;
-                    g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
-                    g.b_resident = 0;
+    // pass 0: weights resident -> tile-major issue order, where ONE set of T accumulators already
+    //         works as a ring (tile t's epilogue overlaps tiles t+1..), so T can use all of TMEM;
+    // pass 1: streamed weights -> weight-stationary order, two accumulator sets.
+    for (int pass = 0; pass < 2 && !placed; ++pass) {
+        for (int cand = want_fold ? 0 : 1; cand < 2 && !placed; ++cand) {
+            const bool fold = cand == 0;
+            const int acc = fold ? 3 * g.cout : g.cout;
+            const int nsets = pass == 0 ? 1 : ((!fold && g.cout >= 256) ? 1 : 2);
+            int tmax = (512 / nsets) / acc;
+            if (tmax < 1) continue;
+            if (fold) { g.P = 32; g.Ht = 4; }
+            else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+            g.plane_rows = (g.Ht + 2) * g.P;
+            g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
+            if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
+            if (tmax > g.D) tmax = g.D;
+            for (; tmax >= 1 && !placed; --tmax) {
+                const int ngr = (g.D + tmax - 1) / tmax;
+                const int T = (g.D + ngr - 1) / ngr;
+                const long avail = budget - (long)(T + 2) * g.plane_bytes;
+                if (avail <= 0) continue;
+                if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
+                    g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
+                    g.b_resident = 1;
                     placed = true;
-                    break;
+                } else if (pass == 1 && (!fold || T >= 2)) {
+                    for (int G : {9, 3, 1}) {
+                        if (fold && G == 1) continue;
+                        const long sb = (long)G * tap_bytes;
+                        if (sb > 36 * 1024 && G > 1) continue;
+                        long nb = avail / sb;
+                        if (nb < 2) continue;
+                        if (nb > 6) nb = 6;
+                        g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
+                        g.b_resident = 0;
+                        placed = true;
+                        break;
+                    }
                 }
-            }
-            if (placed) {
-                g.nsets = nsets;
-                g.acc_cols = acc;
-                t.fold = fold ? 1 : 0;
+                if (placed) {
+                    g.nsets = nsets;
+                    g.acc_cols = acc;
+                    t.fold = fold ? 1 : 0;
+                }
+                if (pass == 0 && !placed && T <= 2) break;      // resident only pays with a few tiles per group
             }
         }
     }
