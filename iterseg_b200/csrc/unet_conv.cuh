@@ -115,15 +115,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < g.T + 2; ++i) {
             mbar_init(&plane_full[i], 1);
-            mbar_init(&plane_empty[i], 1);
+            mbar_init(&plane_empty[i], 2);        // both MMA-issuing warps commit
         }
         for (int i = 0; i < g.T * g.nsets; ++i) {
-            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_full[i], 2);
             mbar_init(&acc_empty[i], 4);
         }
         for (int i = 0; i < g.n_b_stages; ++i) {
             mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], 1);
+            mbar_init(&b_empty[i], 2);
         }
         fence_barrier_init();
     }
@@ -197,14 +197,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuers (two warps) =====================
+        // Tiles are split by parity between warps 1 and 2 (different SM sub-partitions): one
+        // thread issuing every tcgen05.mma of the CTA is what bounded the previous version.  A
+        // tile's accumulator is only ever touched by one issuer, so no ordering between the two
+        // is needed; BOTH warps walk the identical loops and commit to every barrier (count 2) --
+        // a commit covers the MMAs its own thread issued, and each warp reaches a release point
+        // only after its own last use of that plane / weight stage.
         // The whole warp walks the loops (so that all the address arithmetic is warp-uniform)
         // and one elected lane issues; what bounds thin layers is the instruction count per
         // tcgen05.mma: descriptors are (constant high word) | (start address >> 4) and the tap
         // loops are fully unrolled, leaving ~2 integer adds per MMA.
         {
             const bool leader = elect_one();
+            const int par = warp - 1;                          // this issuer's tiles: t % 2 == par
             const uint32_t idesc = make_idesc_f16(128, (uint32_t)g.acc_cols, 0 /* fp16 */);
             const uint32_t nb = (uint32_t)g.n_b_stages;
             uint32_t plane_ph = 0, acc_ph = 0;
@@ -243,7 +250,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (!b_waited)
                                 for (int bg = 0; bg < NBG; ++bg) mbar_wait(&b_full[kb * NBG + bg], 0u);
                             tc_fence_after();
-                            if (leader) {
+                            if (leader && (t & 1) == par) {
                                 const uint32_t b_kb = b_lo0 + (uint32_t)(kb * NBG) * b_stage_units;
 #pragma unroll
                                 for (int tap = 0; tap < 27; tap += (FOLD ? 3 : 1)) {
@@ -257,6 +264,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                         umma_f16(tmem_d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
                                     }
                                 }
+                            }
+                            if (leader) {
                                 umma_commit(&plane_empty[t]);                 // last use of plane t
                                 if (t == tg - 1) {
                                     umma_commit(&plane_empty[tg]);
@@ -288,7 +297,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 ++ready;
                             }
                             tc_fence_after();
-                            if (leader) {
+                            if (leader && (t & 1) == par) {
 #pragma unroll
                                 for (int j = 0; j < G; j += (FOLD ? 3 : 1)) {
                                     const int tap0 = bg * G;
@@ -303,6 +312,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                                  (bg | j | k) != 0 ? 1u : (kb != 0 ? 1u : 0u));
                                     }
                                 }
+                            }
+                            if (leader) {
                                 if (bg == NBG - 1) {
                                     umma_commit(&plane_empty[t + 2]);          // last use of plane t+2
                                     if (kb == nkb - 1) umma_commit(&acc_full[a0 + t]);
