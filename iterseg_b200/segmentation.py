@@ -203,6 +203,9 @@ def segmentation_loop(viewer, data, chunk_size, margin, output_labels, processin
         output_labels[...] = output
         yield 0
         return
+    if _can_pipeline(processing_function, config, data):
+        yield from _pipelined_series(data, chunk_size, margin, output_labels, config)
+        return
     for t in range(data.shape[0]):
         if np.any(output_labels[t]):
             continue
@@ -211,6 +214,56 @@ def segmentation_loop(viewer, data, chunk_size, margin, output_labels, processin
                                                processing_function)
         output_labels[t, ...] = current_output
         yield t
+
+
+def _can_pipeline(processing_function, config, data):
+    return (processing_function is affinity_watershed_for_chunks and data.ndim == 4 and data.shape[0] > 1
+            and isinstance(config.get('unet'), unet_mod.UNet) and config.get('output_volume') is not None
+            and os.environ.get('ISG_NO_PIPELINE') is None)
+
+
+def _pipelined_series(data, chunk_size, margin, output_labels, config):
+    """The frame loop of `segmentation_loop` for our own processing function: identical results
+    and yield order, but two frames in flight -- the host-side preparation (float32 cast, zero-
+    slice strip, `vol /= max`, segmentation.py:877,887-889) and the H2D copy of frame t+1 and the
+    U-Net of frame t+1 overlap the post stage and the D2H copy of frame t
+    (iterseg_b200/pipeline.py)."""
+    from .pipeline import FramePipeline
+    net = config['unet']
+    dev = net.device
+    todo = [t for t in range(data.shape[0]) if not np.any(output_labels[t])]       # warm restart (:875-876)
+    pipe, pending = None, []          # pending: (t, frame shape) of submitted frames, oldest first
+
+    def prepare(t):
+        vol = np.asarray(data[t]).astype(np.float32)
+        if vol.min() == 0:
+            vol = remove_sum_zero_slices(vol)
+        vol /= np.max(vol)
+        return torch.from_numpy(vol).to(dev, non_blocking=True)
+
+    def finish():
+        t_done, shape = pending.pop(0)
+        lab, counts = pipe.collect()
+        LAST_COUNTS['counts'] = counts
+        pipe.drain_to()
+        out = lab[1:-1, 1:-1, 1:-1].cpu().numpy().view(np.uint32)
+        output_labels[t_done, ...] = out
+        return t_done
+
+    for t in todo:
+        frame = prepare(t)
+        if pipe is not None and tuple(frame.shape) != pipe.shape:      # zero-slice strip changed the shape
+            while pending:
+                yield finish()
+            pipe = None
+        if pipe is None:
+            pipe = FramePipeline(net, tuple(frame.shape), tuple(int(c) for c in chunk_size), margin)
+        pipe.submit(frame)
+        pending.append((t, tuple(frame.shape)))
+        if len(pending) == 2:
+            yield finish()
+    while pending:
+        yield finish()
 
 
 def segment_single_volume(input_volume, chunk_size, config, margin, processing_function):
