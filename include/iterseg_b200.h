@@ -160,6 +160,17 @@ int isg_relabel_by_keys(uint32_t *labels, int64_t n, const unsigned long long *l
                         int64_t n_local, const unsigned long long *global_sorted_keys,
                         int64_t n_global, uint32_t *lut_scratch, int *missing_out, void *stream);
 
+/* ---- assessment metrics (src/iterseg/metrics.py:107, :205-227) -------------
+ * gt / seg: n uint32 labels each (device).  out8 (device doubles):
+ *   [0] H(seg|gt)  [1] H(gt|seg)   (variation of information, log base 2, background included)
+ *   [2] TP = label pairs (both non-zero) with IoU > iou_threshold (>= 0.5: one-to-one by itself)
+ *   [3] number of seg objects   [4] number of gt objects   (FP = [3]-[2], FN = [4]-[2])
+ * max_label: upper bound of both label sets (sizes the area tables). */
+size_t isg_metrics_workspace_bytes(int64_t n, int64_t max_label);
+int isg_label_metrics(const uint32_t *gt, const uint32_t *seg, int64_t n, int64_t max_label,
+                      double iou_threshold, double *out8, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* ---- 3-D U-Net over chunks ----------------------------------------------
  * Replaces process_chunks + predict_chunk_feature_map + UNet.forward
  * (predict.py:64-126, unet.py:284-364) for the bundled architecture

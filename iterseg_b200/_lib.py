@@ -40,6 +40,8 @@ SIGNATURES = {
     'isg_sort_tmp_bytes': (_sz, [_i64]),
     'isg_sort_keys_u64': (_i32, [_vp, _i64, _vp, _sz, _vp]),
     'isg_relabel_by_keys': (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'isg_metrics_workspace_bytes': (_sz, [_i64, _i64]),
+    'isg_label_metrics': (_i32, [_vp, _vp, _i64, _i64, _c.c_double, _vp, _vp, _sz, _vp]),
     'isg_unet_packed_weight_bytes': (_sz, []),
     'isg_unet_weights_pack': (_i32, [_vp, _i32, _vp, _vp]),
     'isg_unet_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32]),

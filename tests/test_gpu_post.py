@@ -176,3 +176,27 @@ def test_constant_centre_map_has_no_seeds(ws):
     feats[4] = 0.5
     seg, seeds, mask = ws.segment_output_image(feats, (0, 1, 2), 4, 3)
     assert len(seeds) == 0 and not np.asarray(seg).any()
+
+
+def test_gpu_metrics_equal_oracle():
+    """VI and IoU-matched TP/FP/FN on the device == the oracle's scipy restatement (metrics.py)."""
+    from iterseg_b200 import metrics, synth
+    from oracle import metrics as om
+    gt = synth.platelet_labels((16, 128, 128), seed=2).astype(np.uint32)
+    rng = np.random.default_rng(0)
+    seg = gt.copy()
+    ids = np.unique(gt)[1:]
+    seg[np.isin(gt, ids[:5])] = 0                               # false negatives
+    seg[np.isin(gt, ids[5:9])] = ids[5]                         # a merge
+    seg[2:4, 5:9, 5:9] = gt.max() + 7                           # a false positive
+    perm = rng.permutation(int(seg.max()) + 1).astype(np.uint32); perm[0] = 0
+    seg = perm[seg]                                             # label permutation must not matter
+    m = metrics.label_metrics(gt, seg)
+    want_vi = om.variation_of_information(gt, seg)
+    assert np.allclose([m['vi_seg_given_gt'], m['vi_gt_given_seg']], want_vi, rtol=1e-9, atol=1e-12)
+    assert (m['tp'], m['fp'], m['fn']) == om.matched_counts(gt, seg)
+    assert m['f1'] == pytest.approx(om.matched_f1(gt, seg))
+    same = metrics.label_metrics(gt, gt)
+    assert same['f1'] == 1.0 and same['vi_seg_given_gt'] == 0.0 and same['vi_gt_given_seg'] == 0.0
+    with pytest.raises(Exception):
+        metrics.matched_counts(gt, seg, 0.3)
