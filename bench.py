@@ -83,7 +83,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: the sampler itself is started before the warm-up so that
+        nvidia-smi is up by then; only samples taken after mark() count."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -96,7 +101,14 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t_mark = getattr(self, 't_mark', 0.0)
+        rows = [r for ts, r in self.rows if ts >= t_mark]
+        window = 'timed region'
+        if not rows and self.rows:            # a very short timed region: the last samples under load
+            rows = [r for ts, r in self.rows[-3:]]
+            window = 'warm-up (timed region shorter than the sampling period)'
+        self.window = window
+        for r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 7:
                 continue
@@ -110,7 +122,7 @@ class ClockSampler:
                     reasons.add(n)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(max(smax)) if smax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 # --------------------------------------------------------------------------------------
@@ -248,13 +260,14 @@ def run_gpu(args, rank, local_rank, world):
             all_counts = idist.gather_label_counts({rank: n_local}, world, rank, world, device=dev)
             idist.add_label_offset_host(cur, int(idist.exclusive_offsets(all_counts)[rank]))
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # before the warm-up: nvidia-smi needs ~0.2 s to come up
     counts = steps_device(max(args.warmup, 1))
     barrier()
     plan = list(net._plans.values())[0]
     _lib.check(lib.isg_unet_plan_profile(plan.ptr, 1), 'profile')
     launches0 = lib.isg_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
