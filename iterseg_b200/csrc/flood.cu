@@ -37,7 +37,8 @@ __global__ void domain_kernel(const uint8_t *__restrict__ mask, const uint32_t *
 __global__ void seed_key_kernel(const int64_t *__restrict__ seeds, int64_t n,
                                 const uint32_t *__restrict__ n_dev,
                                 const uint32_t *__restrict__ parent, uint64_t npix,
-                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                const uint32_t *__restrict__ seed_labels) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const bool live = n_dev == nullptr || i < (int64_t)*n_dev;
@@ -48,7 +49,7 @@ __global__ void seed_key_kernel(const int64_t *__restrict__ seeds, int64_t n,
         if (r != CCL_NONE) k = ((uint64_t)r << 32) | (uint64_t)s;
     }
     keys[i] = k;
-    vals[i] = (uint32_t)(i + 1);
+    vals[i] = seed_labels ? seed_labels[i] : (uint32_t)(i + 1);
 }
 
 // Single CTA: split the sorted seed list into components, give single-seed
@@ -239,6 +240,7 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
     b->evals_a = cv.take<uint32_t>(b->edge_cap);
     b->evals_b = cv.take<uint32_t>(b->edge_cap);
     b->seedpos = cv.take<uint32_t>(max_seeds);
+    b->seedgs = cv.take<uint32_t>(max_seeds);
     b->complab = cv.take<uint32_t>(max_seeds);
     {
         cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
@@ -280,7 +282,7 @@ static FloodStreams *flood_streams() {
 int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uint8_t *mask,
                     const uint32_t *parent, const uint32_t *comp_size, uint32_t *comp_label,
                     const int64_t *seeds, int64_t n_seeds, const uint32_t *n_seeds_dev,
-                    uint32_t *labels, cudaStream_t st) {
+                    uint32_t *labels, cudaStream_t st, const uint32_t *seed_labels) {
     const uint64_t npix = (uint64_t)geom.zp * geom.yp * geom.xp;
     ISG_CUDA(cudaMemsetAsync(b.scalars, 0, 64 * sizeof(uint32_t), st));
     if (n_seeds <= 0) return ISG_OK;
@@ -289,7 +291,7 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     ISG_CUDA(cudaMemsetAsync(b.ccursor, 0, (size_t)n_seeds * sizeof(uint32_t), st));
     int blocks = (int)((n_seeds + 255) / 256);
     seed_key_kernel<<<blocks, 256, 0, st>>>(seeds, n_seeds, n_seeds_dev, parent, npix, b.keys_a,
-                                            b.vals_a);
+                                            b.vals_a, seed_labels);
     ISG_LAUNCHED();
     size_t cub_bytes = b.cub_bytes;
     ISG_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, cub_bytes, b.keys_a, b.keys_b, b.vals_a,
@@ -310,7 +312,7 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
                                                 b.lidmap, b.vox, npix);
     ISG_LAUNCHED();
     seed_edge_kernel<<<blocks, 256, 0, st>>>(b.keys_b, (uint32_t)n_seeds, comp_label, b.comp_start,
-                                             b.ebase, b.ekeys_a, b.evals_a);
+                                             b.ebase, b.ekeys_a, b.evals_a, geom.node_key);
     ISG_LAUNCHED();
     compact_graph_kernel<<<sms * 8, 256, 0, st>>>(geom, parent, comp_label, b.comp_start, b.cbase, b.ebase,
                                                   b.lidmap, b.vox, b.scalars + 12, b.nbr, b.key, b.nlab,
@@ -329,7 +331,7 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
         const int64_t g = n_seeds < (int64_t)sms * 8 ? n_seeds : (int64_t)sms * 8;
         edge_group_kernel<<<(int)g, 256, 0, st>>>(b.scalars, b.ebase, b.cbase, b.comp_start, dk.Current(),
                                                   dv.Current(), reinterpret_cast<uint16_t *>(b.rec),
-                                                  b.seedpos);
+                                                  b.seedpos, b.seedgs, geom.node_key != nullptr);
         ISG_LAUNCHED();
     }
 
@@ -354,6 +356,7 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     bq.lidmap = b.lidmap;
     bq.rec = b.rec;
     bq.seedpos = b.seedpos;
+    bq.seedgs = b.seedgs;
     bq.complab = b.complab;
 
     const size_t smem_xl = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
@@ -382,7 +385,7 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     ISG_LAUNCHED();
     w.work_end = b.scalars + 3;
     flood_heap_kernel<<<grid_for(1), 32, smem_xl, fs->s[0]>>>(w, cg, (uint32_t)FLOOD_SMEM_ENTRIES,
-                                                               b.scalars + 2, labels);
+                                                               b.scalars + 2, labels, geom.node_key);
     ISG_LAUNCHED();
     w.work_end = b.scalars + 7;
     flood_bq_kernel<<<grid_for(4), 32, BQ_SMEM_M, fs->s[1]>>>(w, bq, b.scalars + 6, labels);
@@ -463,6 +466,7 @@ extern "C" int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, in
     g.zp = (uint32_t)zp;
     g.yp = (uint32_t)yp;
     g.xp = (uint32_t)xp;
+    g.node_key = nullptr;
     return flood_stage_run(b, g, mask, parent, comp_size, comp_label, seeds, n_seeds, nullptr, labels,
                            st);
 }

@@ -74,7 +74,8 @@ struct CompactGraph {
 };
 
 __global__ void __launch_bounds__(32)
-flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, uint32_t *labels) {
+flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, uint32_t *labels,
+                  const uint32_t *node_key /* nullable: node-keyed mode */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x;
@@ -106,7 +107,8 @@ flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, 
         for (uint32_t i = lane; i < cnt; i += 32) {
             const uint32_t v = (uint32_t)(w.seed_keys[s0 + i] & 0xFFFFFFFFu);
             const uint32_t lid = cg.lidmap[v];
-            hk_st(i, zero_hi | i);           // ascending array == valid heap
+            // ascending array == valid heap (node-keyed mode: fixed up below)
+            hk_st(i, (node_key ? (uint64_t)__ldg(node_key + v) << 32 : zero_hi) | i);
             hn_st(i, lid);
             __stcg(glab + lid, labels[v]);   // the final seed label (duplicates: largest, set upstream)
         }
@@ -114,6 +116,38 @@ flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, 
         uint32_t age = cnt;
         uint32_t pref_node = NO_NODE32, pref_nb = NO_NODE32;   // speculative adjacency prefetch
         __syncwarp();
+        if (node_key) {
+            // the seeds carry their own keys: establish the heap order (32-ary Floyd build)
+            for (int64_t root = ((int64_t)n - 2) / 32; root >= 0; --root) {
+                uint32_t i = (uint32_t)root;
+                const uint64_t lk = hk_ld(i);
+                const uint32_t ln = hn_ld(i);
+                for (;;) {
+                    const uint32_t c0 = i * 32u + 1u;
+                    if (c0 >= n) break;
+                    const uint32_t ch = c0 + lane;
+                    const uint64_t k = ch < n ? hk_ld(ch) : ~0ull;
+                    const uint32_t hi = (uint32_t)(k >> 32);
+                    const uint32_t mhi = __reduce_min_sync(FULL, hi);
+                    const uint32_t lo = hi == mhi ? (uint32_t)k : 0xFFFFFFFFu;
+                    const uint32_t mlo = __reduce_min_sync(FULL, lo);
+                    const uint64_t mk = ((uint64_t)mhi << 32) | mlo;
+                    if (mk >= lk) break;
+                    const uint32_t wc = c0 + __ffs(__ballot_sync(FULL, hi == mhi && lo == mlo)) - 1;
+                    if (lane == 0) {
+                        hk_st(i, mk);
+                        hn_st(i, hn_ld(wc));
+                    }
+                    __syncwarp();
+                    i = wc;
+                }
+                if (lane == 0) {
+                    hk_st(i, lk);
+                    hn_st(i, ln);
+                }
+                __syncwarp();
+            }
+        }
 
         while (n > 0) {
             // ---- pop the minimum -------------------------------------------------
@@ -134,7 +168,7 @@ flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, 
                 if (nb != NO_NODE32) {
                     // edge key: stored at the popped voxel for the three negative directions,
                     // at the neighbour for the positive ones
-                    const size_t kn = (size_t)(lane < 3 ? p : nb) * 3u + axis;
+                    const size_t kn = node_key ? (size_t)nb * 3u : (size_t)(lane < 3 ? p : nb) * 3u + axis;
                     labn = __ldcg(glab + nb);
                     kord = __ldg(gkey + kn);
                 }
@@ -273,6 +307,7 @@ struct BqGraph {
     const uint32_t *lidmap;        // [npix] voxel -> local id
     const uint4 *rec;              // [total][2] u16 x {6 neighbours, 6 group starts, 4 pad}
     const uint32_t *seedpos;       // [n_seeds] queue position of the i-th sorted seed
+    const uint32_t *seedgs;        // [n_seeds] start of the value group that position belongs to
     uint32_t *complab;             // [n_seeds] final label of the i-th sorted seed
 };
 
@@ -317,7 +352,9 @@ flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
             atomicOr(L0 + (pos >> 5), 1u << (pos & 31u));
             atomicOr(L1 + (pos >> 10), 1u << ((pos >> 5) & 31u));
         }
-        if (lane == 0) tail[g.seedpos[s0]] = (uint16_t)cnt;        // the seeds open the 0.0 group
+        if (lane == 0)                                   // the seeds open their value groups (affinity
+            for (uint32_t i = 0; i < cnt; ++i)             // mode: all of them the 0.0 group)
+                tail[g.seedgs[s0 + i]] += 1;
         __syncwarp();
 
         // asynchronous copy of a node record into this lane's staging slot
@@ -477,7 +514,8 @@ __global__ void __launch_bounds__(256)
 edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__restrict__ ebase,
                   const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ comp_start,
                   const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
-                  uint16_t *__restrict__ rec16, uint32_t *__restrict__ seedpos) {
+                  uint16_t *__restrict__ rec16, uint32_t *__restrict__ seedpos,
+                  uint32_t *__restrict__ seedgs, int node_mode) {
     typedef cub::BlockScan<uint32_t, 256> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ uint32_t carry;
@@ -514,6 +552,17 @@ edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__res
                 const uint32_t id = svals[e0 + i];
                 if (id & BQ_SEED_FLAG) {
                     seedpos[s0 + (id & ~BQ_SEED_FLAG)] = i;
+                    seedgs[s0 + (id & ~BQ_SEED_FLAG)] = start;
+                } else if (node_mode) {
+                    // entry of node j (axis 0 only): every neighbour that can claim j queues it here
+                    const uint32_t j = id / 3u, axis = id - 3u * j;
+                    if (axis == 0) {
+#pragma unroll
+                        for (uint32_t d = 0; d < 6; ++d) {
+                            const uint32_t nb = rec16[(size_t)(b0 + j) * 16u + d];
+                            if (nb != NO_NODE) rec16[(size_t)(b0 + nb) * 16u + 6u + (5u - d)] = (uint16_t)start;
+                        }
+                    }
                 } else {
                     const uint32_t j = id / 3u, axis = id - 3u * j;
                     const uint32_t nb = rec16[(size_t)(b0 + j) * 16u + axis];
@@ -533,7 +582,7 @@ __global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_
                                  const uint32_t *__restrict__ comp_label,
                                  const uint32_t *__restrict__ comp_start,
                                  const uint32_t *__restrict__ ebase, uint32_t *__restrict__ ekeys,
-                                 uint32_t *__restrict__ evals) {
+                                 uint32_t *__restrict__ evals, const uint32_t *__restrict__ node_key) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t k = seed_keys[i];
@@ -544,7 +593,7 @@ __global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_
     const uint32_t e0 = ebase[c];
     if (ebase[c + 1] == e0) return;
     const uint32_t idx = i - comp_start[c];
-    ekeys[e0 + idx] = f32_ord(0.0f);
+    ekeys[e0 + idx] = node_key ? __ldg(node_key + (uint32_t)(k & 0xFFFFFFFFu)) : f32_ord(0.0f);
     evals[e0 + idx] = BQ_SEED_FLAG | idx;
 }
 
@@ -601,7 +650,8 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
     const uint32_t total = *total_dev;
     const uint32_t plane = g.yp * g.xp;
     const uint64_t npix = (uint64_t)plane * g.zp;
-    const float d0 = __ldg(g.div + 0), d1 = __ldg(g.div + 1), d2 = __ldg(g.div + 2);
+    const float d0 = g.node_key ? 1.0f : __ldg(g.div + 0), d1 = g.node_key ? 1.0f : __ldg(g.div + 1),
+                d2 = g.node_key ? 1.0f : __ldg(g.div + 2);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
         const uint32_t v = vox[j];
         const uint32_t r = parent[v];
@@ -615,9 +665,15 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
             id[d] = NO_NODE32;
             if (nb >= 0 && (uint64_t)nb < npix && parent[nb] == r) id[d] = lidmap[nb];
         }
-        const uint32_t k[3] = {f32_ord(flood_key_value(g, 0, d0, g.scale[0], z, y, x)),
-                               f32_ord(flood_key_value(g, 1, d1, g.scale[1], z, y, x)),
-                               f32_ord(flood_key_value(g, 2, d2, g.scale[2], z, y, x))};
+        uint32_t k[3];
+        if (g.node_key) {
+            k[0] = __ldg(g.node_key + v);
+            k[1] = k[2] = 0xFFFFFFFFu;
+        } else {
+            k[0] = f32_ord(flood_key_value(g, 0, d0, g.scale[0], z, y, x));
+            k[1] = f32_ord(flood_key_value(g, 1, d1, g.scale[1], z, y, x));
+            k[2] = f32_ord(flood_key_value(g, 2, d2, g.scale[2], z, y, x));
+        }
         const uint32_t e0 = ebase[c];
         if (ebase[c + 1] != e0) {
             uint32_t h[6];
@@ -629,7 +685,7 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
             const uint32_t eb = e0 + (comp_start[c + 1] - comp_start[c]) + 3u * lid;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                ekeys[eb + a] = id[a] != NO_NODE32 ? k[a] : 0xFFFFFFFFu;
+                ekeys[eb + a] = g.node_key ? k[a] : (id[a] != NO_NODE32 ? k[a] : 0xFFFFFFFFu);
                 evals[eb + a] = 3u * lid + a;
             }
         } else {

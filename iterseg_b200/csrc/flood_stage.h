@@ -15,6 +15,10 @@ struct FloodGeom {
     const float *div;          // device float[3]
     float scale[3];
     uint32_t zp, yp, xp;
+    // node-keyed mode (classic marker watershed of the DoG blob path): when non-null, a voxel is
+    // queued with node_key[voxel] (order-preserving uint32, smaller pops first) instead of the
+    // affinity of the edge it was claimed through, and seeds enter with their own key (not 0.0)
+    const uint32_t *node_key;
 };
 
 struct FloodStageBuffers {
@@ -36,7 +40,7 @@ struct FloodStageBuffers {
     uint32_t *ebase;                                             // edge-arena segment per component
     uint32_t *ekeys_a, *ekeys_b, *evals_a, *evals_b;             // edge arena (sort double buffers)
     uint64_t edge_cap;
-    uint32_t *seedpos, *complab;
+    uint32_t *seedpos, *seedgs, *complab;
     unsigned char *seg_tmp;
     size_t seg_bytes;
 };
@@ -53,9 +57,11 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
 // comp_size: voxels per root; comp_label: zeroed scratch indexed by root;
 // seeds: padded flat indices in label order, labels[seed] already set; n_seeds is the
 // host-side (upper bound on the) count, n_seeds_dev the exact device-side count or NULL.
+// seed_labels: NULL (seed i carries label i + 1) or the label of every seed (several seeds may
+// share one: multi-voxel markers).
 int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uint8_t *mask,
                     const uint32_t *parent, const uint32_t *comp_size, uint32_t *comp_label,
                     const int64_t *seeds, int64_t n_seeds, const uint32_t *n_seeds_dev,
-                    uint32_t *labels, cudaStream_t st);
+                    uint32_t *labels, cudaStream_t st, const uint32_t *seed_labels = nullptr);
 
 }  // namespace isg

@@ -546,6 +546,7 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     g.zp = Z + 2;
     g.yp = Y + 2;
     g.xp = X + 2;
+    g.node_key = nullptr;
     int rc = flood_stage_run(b.flood, g, mask_out, b.parent, b.comp_size, b.comp_label, seeds_out,
                              (int64_t)n_cand, b.scal + 4, labels, st);
     if (rc != ISG_OK) return rc;

@@ -114,3 +114,83 @@ int64_t isg_oracle_flood(const float *image, int64_t npix,
     free(h.d);
     return age;
 }
+
+/* ---------------------------------------------------------------------------
+ * Node-keyed priority flood: the classic marker watershed the DoG blob path calls
+ * (skimage.segmentation.watershed(image, markers, mask=mask), connectivity 1, no
+ * compactness; reference call site src/iterseg/segmentation.py:646).
+ *
+ * scikit-image (not available here; restated from _watershed_cy.pyx::watershed_raveled):
+ *   every marker voxel is pushed in raveled order with value image[index], age 0; pop the
+ *   smallest (value, age); for the neighbours in the order of `offsets`: skip if not in
+ *   mask or already labelled, else age += 1, label it with the popped voxel's label and
+ *   push it with value image[neighbour] and that age.
+ * PARITY UNPINNED in one respect: markers of equal value all carry age 0, and the order
+ * in which scikit-image's binary heap pops them is an artefact of its sift routines.
+ * Here (and in the CUDA kernel) equal-valued markers pop in raveled-index order.
+ * key: int64 values, smaller pops first (the caller maps -distance to them).
+ */
+typedef struct {
+    int64_t value;
+    int64_t age;
+    int64_t index;
+} nelem_t;
+
+static inline int nelem_less(const nelem_t *a, const nelem_t *b) {
+    if (a->value != b->value) return a->value < b->value;
+    if (a->age != b->age) return a->age < b->age;
+    return a->index < b->index;
+}
+
+int64_t isg_oracle_node_flood(const int64_t *image, int64_t npix, const int64_t *offsets,
+                              int64_t n_offsets, const uint8_t *mask, int32_t *output) {
+    nelem_t *h = NULL;
+    int64_t n = 0, cap = 0, age = 0;
+#define NPUSH(e)                                                                      \
+    do {                                                                              \
+        if (n == cap) {                                                               \
+            cap = cap ? cap * 2 : 1024;                                               \
+            nelem_t *nd = (nelem_t *)realloc(h, (size_t)cap * sizeof(nelem_t));       \
+            if (!nd) { free(h); return -1; }                                          \
+            h = nd;                                                                   \
+        }                                                                             \
+        int64_t i_ = n++;                                                             \
+        while (i_ > 0) {                                                              \
+            int64_t p_ = (i_ - 1) >> 1;                                               \
+            if (!nelem_less(&(e), &h[p_])) break;                                     \
+            h[i_] = h[p_];                                                            \
+            i_ = p_;                                                                  \
+        }                                                                             \
+        h[i_] = (e);                                                                  \
+    } while (0)
+    for (int64_t v = 0; v < npix; ++v)
+        if (output[v]) {
+            nelem_t e = {image[v], 0, v};
+            NPUSH(e);
+        }
+    while (n > 0) {
+        nelem_t top = h[0];
+        nelem_t last = h[--n];
+        int64_t i = 0;
+        for (;;) {
+            int64_t c = 2 * i + 1;
+            if (c >= n) break;
+            if (c + 1 < n && nelem_less(&h[c + 1], &h[c])) c++;
+            if (!nelem_less(&h[c], &last)) break;
+            h[i] = h[c];
+            i = c;
+        }
+        if (n > 0) h[i] = last;
+        for (int64_t k = 0; k < n_offsets; ++k) {
+            int64_t nb = top.index + offsets[k];
+            if (nb < 0 || nb >= npix || !mask[nb] || output[nb]) continue;
+            ++age;
+            output[nb] = output[top.index];
+            nelem_t e = {image[nb], age, nb};
+            NPUSH(e);
+        }
+    }
+#undef NPUSH
+    free(h);
+    return age;
+}
