@@ -160,6 +160,33 @@ int isg_relabel_by_keys(uint32_t *labels, int64_t n, const unsigned long long *l
                         int64_t n_local, const unsigned long long *global_sorted_keys,
                         int64_t n_global, uint32_t *lut_scratch, int *missing_out, void *stream);
 
+/* ---- DoG blob segmenter ------------------------------------------------------
+ * Replaces dog_blob_watershed_for_chunks + dog_image (segmentation.py:592-650, :678-680).
+ *   vol          (Z,Y,X) float32 frame (the function pads it by one voxel itself, :634)
+ *   params       Gaussian half kernels (float64, scipy's) and radii of, in order:
+ *                  [0] min_sigma 'nearest'  [1] max_sigma 'nearest'   (the mask, dog_image)
+ *                  [2] sigma_list[0] 'reflect'  [3] sigma_list[1] 'reflect'   (blob_dog, one DoG layer)
+ *                threshold (mask and blob threshold), scale_factor = 1/(sigma_ratio-1),
+ *                prune_d2 / prune_radius: largest squared lattice distance at which two blobs of
+ *                sigma_list[0] overlap by more than 0.5 (_prune_blobs) and its integer radius
+ *   labels       (Z+2,Y+2,X+2) uint32, zero on entry: markers + watershed result, in place
+ *   mask_out     (Z+2,Y+2,X+2) uint8: dog > threshold
+ *   distance_out optional (Z+2,Y+2,X+2) float64: ndi.distance_transform_edt(padded volume)
+ *   counts_out   device int64[4]: {peak candidates, blobs after pruning, marker voxels, 0}
+ */
+typedef struct {
+    double weights[4][12];
+    int radius[4];
+    float threshold;
+    float scale_factor;
+    int prune_d2;
+    int prune_radius;
+} isg_dog_params;
+size_t isg_dog_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds);
+int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int64_t x, const isg_dog_params *params,
+                         uint32_t *labels, uint8_t *mask_out, double *distance_out, int64_t max_seeds,
+                         int64_t *counts_out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- assessment metrics (src/iterseg/metrics.py:107, :205-227) -------------
  * gt / seg: n uint32 labels each (device).  out8 (device doubles):
  *   [0] H(seg|gt)  [1] H(gt|seg)   (variation of information, log base 2, background included)

@@ -21,6 +21,11 @@ class PostParams(_c.Structure):
                 ('own_z1', _i32), ('open_faces', _i32), ('seed_keys_out', _vp)]
 
 
+class DogParams(_c.Structure):
+    _fields_ = [('weights', (_c.c_double * 12) * 4), ('radius', _i32 * 4), ('threshold', _f32),
+                ('scale_factor', _f32), ('prune_d2', _i32), ('prune_radius', _i32)]
+
+
 # name -> (restype, argtypes); this table is also what the symbol-export test checks
 SIGNATURES = {
     'isg_version': (_i32, []),
@@ -40,6 +45,9 @@ SIGNATURES = {
     'isg_sort_tmp_bytes': (_sz, [_i64]),
     'isg_sort_keys_u64': (_i32, [_vp, _i64, _vp, _sz, _vp]),
     'isg_relabel_by_keys': (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'isg_dog_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
+    'isg_dog_blob_segment': (_i32, [_vp, _i64, _i64, _i64, _c.POINTER(DogParams), _vp, _vp, _vp, _i64, _vp,
+                                    _vp, _sz, _vp]),
     'isg_metrics_workspace_bytes': (_sz, [_i64, _i64]),
     'isg_label_metrics': (_i32, [_vp, _vp, _i64, _i64, _c.c_double, _vp, _vp, _sz, _vp]),
     'isg_unet_packed_weight_bytes': (_sz, []),

@@ -1,0 +1,443 @@
+// DoG blob segmenter on the device: isg_dog_blob_segment.
+//
+// Replaces dog_blob_watershed_for_chunks + dog_image (src/iterseg/segmentation.py:592-650,
+// :678-680):
+//   input_volume = np.pad(input_volume, 1)                                       :634
+//   mask    = gaussian(v, min_sigma) - gaussian(v, max_sigma) > threshold        :635-636, :678-680
+//   markers = blob_dog(v, min_sigma, max_sigma, threshold)                        :637-638
+//   distance = ndi.distance_transform_edt(v)                                      :639
+//   markers, n = ndi.label(centroids at the blob coordinates)                     :641-644
+//   labels  = watershed(-distance, markers, mask=mask)                            :645
+// The three scikit-image functions are restated from their published algorithms (scikit-image
+// is not available in the build environment; parity unpinned, see oracle/dog.py for the
+// exact statements and the two documented tie rules).  Arithmetic contracts as in post.cu:
+// every 1-D Gaussian pass accumulates in float64 in scipy's order and stores float32.
+//   * Gaussians: separable, 'nearest' for the mask, 'reflect' for blob_dog;
+//   * blob_dog with one DoG layer (k = int(log(max/min)/log(1.6) + 1) == 1, i.e.
+//     max_sigma / min_sigma < 1.6): 3x3x3 maxima of (G(s0) - G(1.6 s0)) / 0.6 above the
+//     threshold, no border exclusion, a constant cube has none; _prune_blobs with one common
+//     sigma reduces to "a blob dies iff a LATER blob (peak order) lies within the overlap
+//     distance" (pairs walked in lexicographic order), which is data parallel;
+//   * exact Euclidean distance transform: separable squared-distance passes (x scan, then z
+//     and y lower envelopes by bounded search); the flood is keyed by ~d2 (uint32), which orders
+//     voxels exactly like float64 -sqrt(d2);
+//   * ndi.label numbering: 6-connected components of the marker voxels, ids in raster order of
+//     each component's first voxel;
+//   * the marker watershed: flood_stage_run in node-keyed mode (flood.cuh).
+#include <cub/cub.cuh>
+
+#include "flood_stage.h"
+
+namespace isg {
+
+struct GaussD {
+    double w[12];
+    int r;
+};
+
+// one axis of scipy.ndimage.gaussian_filter (correlate1d, symmetric kernel), mode 0 = 'nearest',
+// 1 = 'reflect' (d c b a | a b c d | d c b a)
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+dog_gauss_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t Z, uint32_t Y, uint32_t X,
+                 GaussD gw, int reflect) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int len = (int)(AXIS == 0 ? Z : (AXIS == 1 ? Y : X));
+    const uint64_t step = AXIS == 0 ? (uint64_t)Y * X : (AXIS == 1 ? (uint64_t)X : 1ull);
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint32_t x = (uint32_t)(v % X);
+        const uint64_t t = v / X;
+        const uint32_t y = (uint32_t)(t % Y), z = (uint32_t)(t / Y);
+        const int c = (int)(AXIS == 0 ? z : (AXIS == 1 ? y : x));
+        const uint64_t line0 = v - (uint64_t)c * step;
+        auto at = [&](int i) -> double {
+            if (reflect) {
+                while (i < 0 || i >= len) i = i < 0 ? -i - 1 : 2 * len - i - 1;
+            } else {
+                i = i < 0 ? 0 : (i >= len ? len - 1 : i);
+            }
+            return (double)__ldg(in + line0 + (uint64_t)i * step);
+        };
+        double acc = __dmul_rn((double)in[v], gw.w[0]);
+        for (int j = gw.r; j >= 1; --j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(at(c - j), at(c + j)), gw.w[j]));
+        out[v] = (float)acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pad_kernel(const float *__restrict__ vol, float *__restrict__ vp, uint32_t Z, uint32_t Y, uint32_t X) {
+    const uint32_t Yp = Y + 2, Xp = X + 2;
+    const uint64_t np = (uint64_t)(Z + 2) * Yp * Xp;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < np; v += stride) {
+        const uint32_t x = (uint32_t)(v % Xp);
+        const uint64_t t = v / Xp;
+        const uint32_t y = (uint32_t)(t % Yp), z = (uint32_t)(t / Yp);
+        float o = 0.0f;
+        if (x >= 1 && x <= X && y >= 1 && y <= Y && z >= 1 && z <= Z)
+            o = __ldg(vol + ((uint64_t)(z - 1) * Y + (y - 1)) * X + (x - 1));
+        vp[v] = o;
+    }
+}
+
+// mask = a - b > thr;  cube = (c - d) * sf (float32 arithmetic, as numpy evaluates it)
+__global__ void __launch_bounds__(256)
+dog_combine_kernel(const float *__restrict__ a, const float *__restrict__ b, float thr,
+                   uint8_t *__restrict__ mask, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        mask[v] = __fsub_rn(a[v], b[v]) > thr ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+dog_cube_kernel(const float *__restrict__ c, const float *__restrict__ d, float sf, float *__restrict__ cube,
+                uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        cube[v] = __fmul_rn(__fsub_rn(c[v], d[v]), sf);
+}
+
+// 3x3x3 maxima ('nearest' = clamped window), value > thr, no border exclusion
+__global__ void __launch_bounds__(256)
+dog_peak_kernel(const float *__restrict__ cs, uint32_t Z, uint32_t Y, uint32_t X, float thr,
+                uint64_t *__restrict__ cand, uint32_t cap, uint32_t *__restrict__ n_cand,
+                uint32_t *__restrict__ nontrivial) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool saw_nonmax = false;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint32_t x = (uint32_t)(v % X);
+        const uint64_t t = v / X;
+        const uint32_t y = (uint32_t)(t % Y), z = (uint32_t)(t / Y);
+        const float c = cs[v];
+        bool is_max = true;
+        const uint32_t z0 = z ? z - 1 : 0, z1 = z + 1 < Z ? z + 1 : Z - 1;
+        const uint32_t y0 = y ? y - 1 : 0, y1 = y + 1 < Y ? y + 1 : Y - 1;
+        const uint32_t x0 = x ? x - 1 : 0, x1 = x + 1 < X ? x + 1 : X - 1;
+        for (uint32_t zz = z0; zz <= z1; ++zz)
+            for (uint32_t yy = y0; yy <= y1; ++yy) {
+                const float *row = cs + ((uint64_t)zz * Y + yy) * X;
+                for (uint32_t xx = x0; xx <= x1; ++xx) is_max &= !(__ldg(row + xx) > c);
+            }
+        if (!is_max) saw_nonmax = true;
+        if (is_max && c > thr) {
+            const uint32_t slot = atomicAdd(n_cand, 1u);
+            if (slot < cap) cand[slot] = ((uint64_t)(~f32_ord(c)) << 32) | (uint64_t)v;
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, saw_nonmax) && (threadIdx.x & 31) == 0) atomicOr(nontrivial, 1u);
+}
+
+// blob index grid (rank + 1 in peak order) and the prune rule
+__global__ void blob_grid_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n,
+                                 const uint32_t *__restrict__ nontrivial, uint32_t *__restrict__ grid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || *nontrivial == 0) return;
+    grid[(uint32_t)(cand_sorted[i] & 0xFFFFFFFFu)] = i + 1;
+}
+__global__ void blob_prune_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n,
+                                  const uint32_t *__restrict__ nontrivial, const uint32_t *__restrict__ grid,
+                                  uint32_t Z, uint32_t Y, uint32_t X, int rad, int d2max,
+                                  uint8_t *__restrict__ centroids, uint32_t *__restrict__ n_blobs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || *nontrivial == 0) return;
+    const uint32_t v = (uint32_t)(cand_sorted[i] & 0xFFFFFFFFu);
+    const int x = (int)(v % X), y = (int)((v / X) % Y), z = (int)(v / ((uint64_t)X * Y));
+    bool dies = false;
+    for (int dz = -rad; dz <= rad && !dies; ++dz)
+        for (int dy = -rad; dy <= rad && !dies; ++dy)
+            for (int dx = -rad; dx <= rad; ++dx) {
+                const int q = dz * dz + dy * dy + dx * dx;
+                if (q == 0 || q > d2max) continue;
+                const int zz = z + dz, yy = y + dy, xx = x + dx;
+                if (zz < 0 || yy < 0 || xx < 0 || zz >= (int)Z || yy >= (int)Y || xx >= (int)X) continue;
+                const uint32_t j = grid[((uint64_t)zz * Y + yy) * X + xx];
+                if (j > i + 1) { dies = true; break; }       // a later blob overlaps: this one is pruned
+            }
+    if (!dies) {
+        centroids[v] = 1;
+        atomicAdd(n_blobs, 1u);
+    }
+}
+
+// ---- exact squared Euclidean distance to the nearest zero voxel ------------------------------
+static constexpr uint32_t EDT_INF = 1u << 28;
+// x pass: one thread per row, two sweeps
+__global__ void __launch_bounds__(128)
+edt_x_kernel(const float *__restrict__ vp, uint32_t *__restrict__ d2, uint64_t rows, uint32_t X) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *in = vp + r * X;
+    uint32_t *out = d2 + r * X;
+    uint32_t d = EDT_INF;
+    for (uint32_t x = 0; x < X; ++x) {
+        d = in[x] == 0.0f ? 0u : (d >= EDT_INF ? EDT_INF : d + 1u);
+        out[x] = d;
+    }
+    d = EDT_INF;
+    for (uint32_t x = X; x-- > 0;) {
+        d = in[x] == 0.0f ? 0u : (d >= EDT_INF ? EDT_INF : d + 1u);
+        const uint32_t f = out[x] < d ? out[x] : d;
+        out[x] = f >= EDT_INF ? EDT_INF : f * f;
+    }
+}
+// lower envelope along one axis: out[c] = min_j in[j] + (c - j)^2, searched outwards until (c-j)^2 >= best
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+edt_axis_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t Z, uint32_t Y, uint32_t X) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int len = (int)(AXIS == 0 ? Z : Y);
+    const uint64_t step = AXIS == 0 ? (uint64_t)Y * X : (uint64_t)X;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint64_t t = v / X;
+        const int c = (int)(AXIS == 0 ? t / Y : t % Y);
+        const uint64_t line0 = v - (uint64_t)c * step;
+        uint32_t best = in[v];
+        for (int o = 1; o < len; ++o) {
+            const uint32_t oo = (uint32_t)o * (uint32_t)o;
+            if (oo >= best) break;
+            if (c - o >= 0) {
+                const uint32_t a = __ldg(in + line0 + (uint64_t)(c - o) * step);
+                if (a < EDT_INF && a + oo < best) best = a + oo;
+            }
+            if (c + o < len) {
+                const uint32_t a = __ldg(in + line0 + (uint64_t)(c + o) * step);
+                if (a < EDT_INF && a + oo < best) best = a + oo;
+            }
+        }
+        out[v] = best;
+    }
+}
+__global__ void __launch_bounds__(256)
+edt_finish_kernel(const uint32_t *__restrict__ d2, uint32_t *__restrict__ key, double *__restrict__ dist,
+                  uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint32_t q = d2[v];
+        key[v] = ~q;                                   // -distance ascending == d2 descending
+        if (dist) dist[v] = sqrt((double)q);
+    }
+}
+
+// ---- ndi.label numbering of the marker voxels and the seed list -------------------------------
+__global__ void __launch_bounds__(256)
+root_flag_kernel(const uint32_t *__restrict__ parent, uint32_t *__restrict__ flag, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        flag[v] = parent[v] == (uint32_t)v ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+marker_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ rank_excl,
+              uint32_t *__restrict__ labels, int64_t *__restrict__ seeds, uint32_t *__restrict__ seed_labels,
+              uint32_t cap, uint32_t *__restrict__ n_seeds, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint32_t r = parent[v];
+        if (r == CCL_NONE) continue;
+        const uint32_t l = rank_excl[r] + 1u;
+        labels[v] = l;
+        const uint32_t slot = atomicAdd(n_seeds, 1u);
+        if (slot < cap) {
+            seeds[slot] = (int64_t)v;
+            seed_labels[slot] = l;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+dog_domain_kernel(const uint8_t *__restrict__ mask, const uint8_t *__restrict__ centroids,
+                  uint8_t *__restrict__ dom, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        dom[v] = (mask[v] | centroids[v]) ? 1 : 0;
+}
+__global__ void dog_counts_kernel(const uint32_t *n_cand, const uint32_t *n_blobs, const uint32_t *n_seeds,
+                                  const uint32_t *n_markers_src, uint64_t last, int64_t *out) {
+    out[0] = *n_cand;
+    out[1] = *n_blobs;
+    out[2] = *n_seeds;
+    out[3] = n_markers_src[last];
+}
+
+struct DogBuffers {
+    float *vp, *ga, *gb, *gc;
+    uint32_t *d2a, *d2b, *key, *grid, *flag, *rank;
+    uint64_t *cand_a, *cand_b;
+    uint8_t *centroids, *dom;
+    uint32_t *parent, *comp_size, *comp_label, *seed_labels, *scal;
+    int64_t *seeds;
+    unsigned char *cub_tmp;
+    size_t cub_bytes;
+    FloodStageBuffers flood;
+};
+
+static void dog_carve(DogBuffers *b, Carver &cv, uint64_t np, int64_t max_seeds) {
+    b->vp = cv.take<float>(np);
+    b->ga = cv.take<float>(np);
+    b->gb = cv.take<float>(np);
+    b->gc = cv.take<float>(np);
+    b->d2a = cv.take<uint32_t>(np);
+    b->d2b = cv.take<uint32_t>(np);
+    b->key = cv.take<uint32_t>(np);
+    b->grid = cv.take<uint32_t>(np);
+    b->flag = cv.take<uint32_t>(np);
+    b->rank = cv.take<uint32_t>(np + 1);
+    b->cand_a = cv.take<uint64_t>(max_seeds);
+    b->cand_b = cv.take<uint64_t>(max_seeds);
+    b->centroids = cv.take<uint8_t>(np);
+    b->dom = cv.take<uint8_t>(np);
+    b->parent = cv.take<uint32_t>(np);
+    b->comp_size = cv.take<uint32_t>(np);
+    b->comp_label = cv.take<uint32_t>(np);
+    b->seed_labels = cv.take<uint32_t>(max_seeds);
+    b->seeds = cv.take<int64_t>(max_seeds);
+    b->scal = cv.take<uint32_t>(64);
+    size_t s1 = 0, s2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, s1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)max_seeds);
+    cub::DeviceScan::ExclusiveSum(nullptr, s2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(np + 1));
+    b->cub_bytes = (s1 > s2 ? s1 : s2) + 256;
+    b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
+    flood_stage_workspace(&b->flood, cv, np, max_seeds);
+}
+
+template <int AXIS>
+static int gauss_pass(const float *in, float *out, uint32_t Z, uint32_t Y, uint32_t X, const GaussD &g, int reflect,
+                      cudaStream_t st) {
+    dog_gauss_kernel<AXIS><<<num_sms() * 8, 256, 0, st>>>(in, out, Z, Y, X, g, reflect);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+// 3-axis Gaussian in -> out using tmp (in is preserved)
+static int gauss3(const float *in, float *tmp, float *out, uint32_t Z, uint32_t Y, uint32_t X, const GaussD &g,
+                  int reflect, cudaStream_t st) {
+    int rc = gauss_pass<0>(in, out, Z, Y, X, g, reflect, st);
+    if (rc) return rc;
+    rc = gauss_pass<1>(out, tmp, Z, Y, X, g, reflect, st);
+    if (rc) return rc;
+    return gauss_pass<2>(tmp, out, Z, Y, X, g, reflect, st);
+}
+
+}  // namespace isg
+
+using namespace isg;
+
+extern "C" size_t isg_dog_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds) {
+    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0) return 0;
+    Carver cv(nullptr, 0);
+    DogBuffers b;
+    dog_carve(&b, cv, (uint64_t)(z + 2) * (y + 2) * (x + 2), max_seeds);
+    return cv.off + 512;
+}
+
+extern "C" int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int64_t x,
+                                    const isg_dog_params *prm, uint32_t *labels, uint8_t *mask_out,
+                                    double *distance_out, int64_t max_seeds, int64_t *counts_out,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    ISG_REQUIRE(vol && prm && labels && mask_out && counts_out, ISG_ERR_ARG, "isg_dog_blob_segment: null pointer");
+    ISG_REQUIRE(z >= 1 && y >= 1 && x >= 1 && max_seeds >= 1, ISG_ERR_ARG, "bad extents");
+    for (int i = 0; i < 4; ++i)
+        ISG_REQUIRE(prm->radius[i] >= 0 && prm->radius[i] <= 11, ISG_ERR_ARG, "gaussian radius must be <= 11");
+    const uint32_t Z = (uint32_t)z + 2, Y = (uint32_t)y + 2, X = (uint32_t)x + 2;      // padded extents
+    const uint64_t np = (uint64_t)Z * Y * X;
+    ISG_REQUIRE(np < 0xFFFFFFF0ull, ISG_ERR_OVERFLOW, "volume too large for 32-bit voxel ids");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(workspace, workspace_bytes);
+    DogBuffers b;
+    dog_carve(&b, cv, np, max_seeds);
+    ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE, "isg_dog_blob_segment: workspace too small (%zu < %zu)",
+                workspace_bytes, cv.off);
+    const int grid = num_sms() * 8;
+    GaussD g[4];
+    for (int k = 0; k < 4; ++k) {
+        g[k].r = prm->radius[k];
+        for (int i = 0; i <= prm->radius[k]; ++i) g[k].w[i] = prm->weights[k][i];
+    }
+    ISG_CUDA(cudaMemsetAsync(b.scal, 0, 64 * sizeof(uint32_t), st));
+    pad_kernel<<<grid, 256, 0, st>>>(vol, b.vp, (uint32_t)z, (uint32_t)y, (uint32_t)x);
+    ISG_LAUNCHED();
+    int rc;
+    // ---- mask = gaussian(v, min) - gaussian(v, max) > threshold ('nearest') ------------------
+    if ((rc = gauss3(b.vp, b.gc, b.ga, Z, Y, X, g[0], 0, st))) return rc;
+    if ((rc = gauss3(b.vp, b.gc, b.gb, Z, Y, X, g[1], 0, st))) return rc;
+    dog_combine_kernel<<<grid, 256, 0, st>>>(b.ga, b.gb, prm->threshold, mask_out, np);
+    ISG_LAUNCHED();
+    // ---- blob_dog: one DoG layer of 'reflect' Gaussians, scaled, 3x3x3 maxima ---------------------
+    if ((rc = gauss3(b.vp, b.gc, b.ga, Z, Y, X, g[2], 1, st))) return rc;
+    if ((rc = gauss3(b.vp, b.gc, b.gb, Z, Y, X, g[3], 1, st))) return rc;
+    dog_cube_kernel<<<grid, 256, 0, st>>>(b.ga, b.gb, prm->scale_factor, b.gc, np);
+    ISG_LAUNCHED();
+    dog_peak_kernel<<<grid, 256, 0, st>>>(b.gc, Z, Y, X, prm->threshold, b.cand_a, (uint32_t)max_seeds,
+                                          b.scal + 0, b.scal + 1);
+    ISG_LAUNCHED();
+    uint32_t n_cand = 0;
+    ISG_CUDA(cudaMemcpyAsync(&n_cand, b.scal + 0, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ISG_CUDA(cudaStreamSynchronize(st));
+    ISG_REQUIRE(n_cand <= (uint64_t)max_seeds, ISG_ERR_OVERFLOW,
+                "isg_dog_blob_segment: %u blob candidates exceed max_seeds=%lld", n_cand, (long long)max_seeds);
+    const uint64_t *cand_sorted = b.cand_a;
+    if (n_cand > 1) {
+        size_t cb = b.cub_bytes;
+        ISG_CUDA(cub::DeviceRadixSort::SortKeys(b.cub_tmp, cb, b.cand_a, b.cand_b, (int)n_cand, 0, 64, st));
+        count_launch(4);
+        cand_sorted = b.cand_b;
+    }
+    ISG_CUDA(cudaMemsetAsync(b.grid, 0, np * sizeof(uint32_t), st));
+    ISG_CUDA(cudaMemsetAsync(b.centroids, 0, np, st));
+    if (n_cand > 0) {
+        const int blocks = (int)((n_cand + 255) / 256);
+        blob_grid_kernel<<<blocks, 256, 0, st>>>(cand_sorted, n_cand, b.scal + 1, b.grid);
+        ISG_LAUNCHED();
+        blob_prune_kernel<<<blocks, 256, 0, st>>>(cand_sorted, n_cand, b.scal + 1, b.grid, Z, Y, X,
+                                                  prm->prune_radius, prm->prune_d2, b.centroids, b.scal + 2);
+        ISG_LAUNCHED();
+    }
+    // ---- exact EDT of (v != 0) ----------------------------------------------------------------------
+    edt_x_kernel<<<(int)(((uint64_t)Z * Y + 127) / 128), 128, 0, st>>>(b.vp, b.d2a, (uint64_t)Z * Y, X);
+    ISG_LAUNCHED();
+    edt_axis_kernel<0><<<grid, 256, 0, st>>>(b.d2a, b.d2b, Z, Y, X);
+    ISG_LAUNCHED();
+    edt_axis_kernel<1><<<grid, 256, 0, st>>>(b.d2b, b.d2a, Z, Y, X);
+    ISG_LAUNCHED();
+    edt_finish_kernel<<<grid, 256, 0, st>>>(b.d2a, b.key, distance_out, np);
+    ISG_LAUNCHED();
+    // ---- markers = ndi.label(centroids): raster-order ids -----------------------------------------
+    ISG_CUDA(cudaMemsetAsync(b.comp_size, 0, np * sizeof(uint32_t), st));
+    if ((rc = ccl_run(b.centroids, b.parent, b.comp_size, Z, Y, X, st))) return rc;
+    root_flag_kernel<<<grid, 256, 0, st>>>(b.parent, b.flag, np);
+    ISG_LAUNCHED();
+    {
+        size_t cb = b.cub_bytes;
+        ISG_CUDA(cub::DeviceScan::ExclusiveSum(b.cub_tmp, cb, b.flag, b.rank, (int)np, st));
+        count_launch(2);
+    }
+    marker_kernel<<<grid, 256, 0, st>>>(b.parent, b.rank, labels, b.seeds, b.seed_labels, (uint32_t)max_seeds,
+                                        b.scal + 3, np);
+    ISG_LAUNCHED();
+    // ---- labels = watershed(-distance, markers, mask) ----------------------------------------------
+    dog_domain_kernel<<<grid, 256, 0, st>>>(mask_out, b.centroids, b.dom, np);
+    ISG_LAUNCHED();
+    ISG_CUDA(cudaMemsetAsync(b.comp_size, 0, np * sizeof(uint32_t), st));
+    ISG_CUDA(cudaMemsetAsync(b.comp_label, 0, np * sizeof(uint32_t), st));
+    if ((rc = ccl_run(b.dom, b.parent, b.comp_size, Z, Y, X, st))) return rc;
+    FloodGeom fg;
+    fg.aff = nullptr;
+    fg.plane_stride = 0;
+    fg.origin = 0;
+    fg.za = Z; fg.ya = Y; fg.xa = X;
+    fg.div = nullptr;
+    fg.scale[0] = fg.scale[1] = fg.scale[2] = 1.0f;
+    fg.zp = Z; fg.yp = Y; fg.xp = X;
+    fg.node_key = b.key;
+    uint32_t n_seeds = 0;
+    ISG_CUDA(cudaMemcpyAsync(&n_seeds, b.scal + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ISG_CUDA(cudaStreamSynchronize(st));
+    ISG_REQUIRE(n_seeds <= (uint64_t)max_seeds, ISG_ERR_OVERFLOW, "isg_dog_blob_segment: %u marker voxels exceed max_seeds",
+                n_seeds);
+    // marker voxels were collected with atomics: the flood stage sorts them by (component, index)
+    rc = flood_stage_run(b.flood, fg, mask_out, b.parent, b.comp_size, b.comp_label, b.seeds, (int64_t)n_seeds,
+                         nullptr, labels, st, b.seed_labels);
+    if (rc != ISG_OK) return rc;
+    dog_counts_kernel<<<1, 1, 0, st>>>(b.scal + 0, b.scal + 2, b.scal + 3, b.rank, 0, counts_out);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}

@@ -291,9 +291,107 @@ def remove_sum_zero_slices(input_volume):
 def dog_blob_watershed(napari_viewer, input_volume_layer, save_dir=None, name='labels-prediction',
                        config_file=None, layer_reference=None, chunk_size=(10, 256, 256),
                        margin=(1, 64, 64), debug=False):
-    """Registered for interface parity (segmentation.py:548-589); the DoG blob path is a
-    later row of the scope table and is not built yet."""
-    raise NotImplementedError('DoG-blob-watershed is not implemented in iterseg_b200 yet')
+    """segmentation.py:548-589, same arguments."""
+    return segmentation_wrapper(dog_blob_watershed_for_chunks, dog_blob_watershed_prep_config,
+                                napari_viewer, input_volume_layer, save_dir, name, config_file,
+                                layer_reference, chunk_size, margin, debug)
+
+
+def dog_blob_watershed_prep_config(input_volume_layer, unet_or_config_file, reference_layer,
+                                   max_sigma=1.5, min_sigma=1, threshold=0.02):
+    """segmentation.py:653-675.  (The reference subscripts `config.get[...]`, a TypeError for any
+    config file; here the JSON keys max_sigma / min_sigma / threshold are honoured.)"""
+    if unet_or_config_file is not None:
+        config = read_config_json(unet_or_config_file)
+        max_sigma = config.get('max_sigma', max_sigma) if config.get('max_sigma') is not None else max_sigma
+        min_sigma = config.get('min_sigma', min_sigma) if config.get('min_sigma') is not None else min_sigma
+        threshold = config.get('threshold', threshold) if config.get('threshold') is not None else threshold
+    return {'max_sigma': max_sigma, 'min_sigma': min_sigma, 'threshold': threshold}
+
+
+def _dog_params(min_sigma, max_sigma, threshold, sigma_ratio=1.6, overlap=0.5):
+    import math
+    if not (np.isscalar(min_sigma) and np.isscalar(max_sigma)):
+        raise NotImplementedError('only scalar min_sigma / max_sigma are supported')
+    k = int(math.log(float(max_sigma) / float(min_sigma)) / math.log(sigma_ratio) + 1)
+    if k != 1:
+        raise NotImplementedError(f'blob_dog with {k} DoG layers (max_sigma / min_sigma >= {sigma_ratio}) '
+                                  f'is not implemented: only the single-layer case of the default configuration')
+    s0, s1 = float(min_sigma), float(min_sigma) * sigma_ratio
+    p = _lib.DogParams()
+    for i, sg in enumerate((float(min_sigma), float(max_sigma), s0, s1)):
+        w, r = ws.gaussian_half_kernel(sg)
+        if r > 11:
+            raise ValueError(f'sigma {sg} needs a Gaussian radius of {r} > 11')
+        p.radius[i] = r
+        for j in range(r + 1):
+            p.weights[i][j] = float(w[j])
+    p.threshold = float(threshold)
+    p.scale_factor = float(np.float32(1.0 / (sigma_ratio - 1)))
+    # _prune_blobs: spheres of radius sigma * sqrt(3); blobs closer than this overlap by > `overlap`
+    r = s0 * math.sqrt(3)
+    d2max = 0
+    for d2 in range(1, int((2 * r) ** 2) + 2):
+        d = math.sqrt(d2)
+        if d > 2 * r:
+            break
+        vol = math.pi / (12 * d) * (2 * r - d) ** 2 * (d * d + 4 * d * r)
+        if vol / (4.0 / 3 * math.pi * r ** 3) > overlap:
+            d2max = d2
+    p.prune_d2 = d2max
+    p.prune_radius = int(math.isqrt(d2max)) if d2max else 0
+    return p
+
+
+def dog_blob_segment_device(frame, labels, min_sigma=1, max_sigma=1.5, threshold=0.02, distance=None,
+                            max_seeds=None):
+    """Device core of the DoG blob segmenter: frame (Z,Y,X) float32 CUDA tensor, labels
+    (Z+2,Y+2,X+2) int32 zeros (written in place).  Returns (mask uint8 padded, counts int64[4])."""
+    lib = _lib.load()
+    assert frame.is_cuda and frame.dtype == torch.float32 and frame.is_contiguous()
+    Z, Y, X = (int(v) for v in frame.shape)
+    shape_p = (Z + 2, Y + 2, X + 2)
+    assert tuple(labels.shape) == shape_p and labels.dtype == torch.int32 and labels.is_contiguous()
+    dev = frame.device
+    if max_seeds is None:
+        max_seeds = max(1 << 16, (Z * Y * X) // 8)
+    p = _dog_params(min_sigma, max_sigma, threshold)
+    nbytes = lib.isg_dog_workspace_bytes(Z, Y, X, max_seeds)
+    wsb = ws._workspace('dog', (Z, Y, X, max_seeds), nbytes, dev)
+    mask = torch.empty(shape_p, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    import ctypes
+    with torch.cuda.device(dev):
+        rc = lib.isg_dog_blob_segment(frame.data_ptr(), Z, Y, X, ctypes.byref(p), labels.data_ptr(),
+                                      mask.data_ptr(), distance.data_ptr() if distance is not None else None,
+                                      max_seeds, counts.data_ptr(), wsb.data_ptr(), wsb.numel(),
+                                      _lib.stream_ptr())
+    _lib.check(rc, 'isg_dog_blob_segment')
+    return mask, counts
+
+
+def dog_blob_watershed_for_chunks(input_volume, current_output, chunk_size, margin, min_sigma,
+                                  max_sigma, threshold, **kwargs):
+    """The DoG processing function of the plug-in protocol (segmentation.py:592-650): labels of
+    one frame written IN PLACE into the padded `current_output`.  chunk_size / margin are unused,
+    as in the reference."""
+    _lib.require_device()
+    dev = current_output.device if isinstance(current_output, torch.Tensor) and current_output.is_cuda \
+        else torch.device('cuda', torch.cuda.current_device())
+    vol = input_volume if isinstance(input_volume, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(input_volume, dtype=np.float32))
+    frame = vol.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    shape_p = tuple(int(s) + 2 for s in frame.shape)
+    out_is_dev = isinstance(current_output, torch.Tensor) and current_output.is_cuda
+    labels = current_output.view(shape_p) if out_is_dev else torch.zeros(shape_p, dtype=torch.int32, device=dev)
+    dog_blob_segment_device(frame, labels, min_sigma, max_sigma, threshold)
+    if not out_is_dev:
+        flat = current_output.reshape(-1)
+        if (isinstance(current_output, np.ndarray) and current_output.flags.c_contiguous
+                and current_output.dtype in (np.uint32, np.int32) and current_output.size == labels.numel()):
+            torch.from_numpy(flat.view(np.int32)).copy_(labels.view(-1))
+        else:
+            flat[...] = labels.cpu().numpy().view(np.uint32).reshape(-1).astype(flat.dtype, copy=False)
 
 
 segmenters = {
