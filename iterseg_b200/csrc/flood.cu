@@ -235,19 +235,19 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
     // edge arena of the bucket-queue classes: 3 stored edges per node + one entry per seed
     b->ebase = cv.take<uint32_t>(max_seeds + 1);
     b->edge_cap = npix * 3 + (uint64_t)max_seeds;
-    b->ekeys_a = cv.take<uint32_t>(b->edge_cap);
-    b->ekeys_b = cv.take<uint32_t>(b->edge_cap);
+    b->ekeys_a = cv.take<uint64_t>(b->edge_cap);
+    b->ekeys_b = cv.take<uint64_t>(b->edge_cap);
     b->evals_a = cv.take<uint32_t>(b->edge_cap);
     b->evals_b = cv.take<uint32_t>(b->edge_cap);
     b->seedpos = cv.take<uint32_t>(max_seeds);
     b->seedgs = cv.take<uint32_t>(max_seeds);
     b->complab = cv.take<uint32_t>(max_seeds);
     {
-        cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+        cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
         size_t seg_bytes = 0;
         const int items = (int)(b->edge_cap > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : b->edge_cap);
-        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, seg_bytes, dk, dv, items, (int)max_seeds,
-                                                 (const uint32_t *)nullptr, (const uint32_t *)nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, seg_bytes, dk, dv, items);
         b->seg_bytes = seg_bytes + 256;
         b->seg_tmp = cv.take<unsigned char>(b->seg_bytes);
     }
@@ -318,14 +318,23 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
                                                   b.lidmap, b.vox, b.scalars + 12, b.nbr, b.key, b.nlab,
                                                   b.rec, b.ekeys_a, b.evals_a);
     ISG_LAUNCHED();
-    // rank the edge values of every bucket-queue component (one segment each; stable)
-    cub::DoubleBuffer<uint32_t> dk(b.ekeys_a, b.ekeys_b), dv(b.evals_a, b.evals_b);
+    // rank the edge values of every bucket-queue component: ONE device-wide stable radix sort of
+    // (component << 32 | value) -- component c's entries land exactly in its arena slice
+    // [ebase[c], ebase[c+1]).  The entry count lives on the device: one small read-back.
+    cub::DoubleBuffer<uint64_t> dk(b.ekeys_a, b.ekeys_b);
+    cub::DoubleBuffer<uint32_t> dv(b.evals_a, b.evals_b);
     {
-        size_t sb = b.seg_bytes;
-        const int items = (int)(b.edge_cap > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : b.edge_cap);
-        ISG_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(b.seg_tmp, sb, dk, dv, items, (int)n_seeds,
-                                                          b.ebase, b.ebase + 1, 0, 32, st));
-        count_launch(4);
+        uint32_t total_edges = 0;
+        ISG_CUDA(cudaMemcpyAsync(&total_edges, b.scalars + 13, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ISG_CUDA(cudaStreamSynchronize(st));
+        ISG_REQUIRE((uint64_t)total_edges <= b.edge_cap, ISG_ERR_WORKSPACE, "flood stage: edge arena overflow");
+        if (total_edges > 1) {
+            int comp_bits = 1;
+            while (comp_bits < 32 && (1ll << comp_bits) <= n_seeds) ++comp_bits;
+            size_t sb = b.seg_bytes;
+            ISG_CUDA(cub::DeviceRadixSort::SortPairs(b.seg_tmp, sb, dk, dv, (int)total_edges, 0, 32 + comp_bits, st));
+            count_launch(4);
+        }
     }
     {
         const int64_t g = n_seeds < (int64_t)sms * 8 ? n_seeds : (int64_t)sms * 8;

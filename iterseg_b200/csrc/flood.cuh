@@ -255,7 +255,7 @@ flood_heap_kernel(FloodWork w, CompactGraph cg, uint32_t cap, uint32_t *cursor, 
 // component's edge list (+ one value-0.0 pseudo edge per seed).  The edges are ranked once,
 // in parallel (segmented radix sort of the order-preserving float bits, one segment per
 // component; edge_group_kernel turns ranks into "group start" positions, a group being a
-// run of equal values).  The queue is then a set of POSITIONS:
+// run of equal values).  [The ranking is one device-wide radix sort of (component << 32 | value).]  The queue is then a set of POSITIONS:
 //   push(edge) : position = group start + tail[group]++ ;  slots[position] = node
 //   pop        : the lowest queued position
 // Equal values pop in insertion order because a group's positions are handed out in
@@ -513,7 +513,7 @@ struct MaxU32 {
 __global__ void __launch_bounds__(256)
 edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__restrict__ ebase,
                   const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ comp_start,
-                  const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+                  const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
                   uint16_t *__restrict__ rec16, uint32_t *__restrict__ seedpos,
                   uint32_t *__restrict__ seedgs, int node_mode) {
     typedef cub::BlockScan<uint32_t, 256> Scan;
@@ -531,11 +531,11 @@ edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__res
             // blocked arrangement: thread t owns EG_ITEMS consecutive entries
             const uint32_t i0 = base + t * EG_ITEMS;
             uint32_t gs[EG_ITEMS];
-            uint32_t prev = (i0 > 0 && i0 - 1 < P) ? skeys[e0 + i0 - 1] : 0u;
+            uint64_t prev = (i0 > 0 && i0 - 1 < P) ? skeys[e0 + i0 - 1] : 0ull;
 #pragma unroll
             for (int u = 0; u < EG_ITEMS; ++u) {
                 const uint32_t i = i0 + u;
-                const uint32_t k = i < P ? skeys[e0 + i] : 0u;
+                const uint64_t k = i < P ? skeys[e0 + i] : 0ull;
                 gs[u] = (i > 0 && i < P && k != prev) ? i : 0u;
                 prev = k;
             }
@@ -581,7 +581,7 @@ edge_group_kernel(const uint32_t *__restrict__ n_comp_dev, const uint32_t *__res
 __global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_t n,
                                  const uint32_t *__restrict__ comp_label,
                                  const uint32_t *__restrict__ comp_start,
-                                 const uint32_t *__restrict__ ebase, uint32_t *__restrict__ ekeys,
+                                 const uint32_t *__restrict__ ebase, uint64_t *__restrict__ ekeys,
                                  uint32_t *__restrict__ evals, const uint32_t *__restrict__ node_key) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -593,7 +593,8 @@ __global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_
     const uint32_t e0 = ebase[c];
     if (ebase[c + 1] == e0) return;
     const uint32_t idx = i - comp_start[c];
-    ekeys[e0 + idx] = node_key ? __ldg(node_key + (uint32_t)(k & 0xFFFFFFFFu)) : f32_ord(0.0f);
+    ekeys[e0 + idx] = ((uint64_t)c << 32) |
+                      (node_key ? __ldg(node_key + (uint32_t)(k & 0xFFFFFFFFu)) : f32_ord(0.0f));
     evals[e0 + idx] = BQ_SEED_FLAG | idx;
 }
 
@@ -646,7 +647,7 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
                      const uint32_t *__restrict__ lidmap, const uint32_t *__restrict__ vox,
                      const uint32_t *__restrict__ total_dev, uint32_t *__restrict__ nbr,
                      uint32_t *__restrict__ key, uint32_t *__restrict__ lab, uint4 *__restrict__ rec,
-                     uint32_t *__restrict__ ekeys, uint32_t *__restrict__ evals) {
+                     uint64_t *__restrict__ ekeys, uint32_t *__restrict__ evals) {
     const uint32_t total = *total_dev;
     const uint32_t plane = g.yp * g.xp;
     const uint64_t npix = (uint64_t)plane * g.zp;
@@ -685,7 +686,7 @@ compact_graph_kernel(FloodGeom g, const uint32_t *__restrict__ parent,
             const uint32_t eb = e0 + (comp_start[c + 1] - comp_start[c]) + 3u * lid;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                ekeys[eb + a] = g.node_key ? k[a] : (id[a] != NO_NODE32 ? k[a] : 0xFFFFFFFFu);
+                ekeys[eb + a] = ((uint64_t)c << 32) | (g.node_key ? k[a] : (id[a] != NO_NODE32 ? k[a] : 0xFFFFFFFFu));
                 evals[eb + a] = 3u * lid + a;
             }
         } else {

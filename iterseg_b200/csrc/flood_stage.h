@@ -38,7 +38,8 @@ struct FloodStageBuffers {
     uint32_t *lidmap, *vox, *key, *nbr, *nlab;                   // compact component graphs
     uint4 *rec;                                                  // bucket-queue node records
     uint32_t *ebase;                                             // edge-arena segment per component
-    uint32_t *ekeys_a, *ekeys_b, *evals_a, *evals_b;             // edge arena (sort double buffers)
+    uint64_t *ekeys_a, *ekeys_b;                                 // edge arena: (component << 32 | key)
+    uint32_t *evals_a, *evals_b;                                 // (sort double buffers)
     uint64_t edge_cap;
     uint32_t *seedpos, *seedgs, *complab;
     unsigned char *seg_tmp;
