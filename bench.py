@@ -17,6 +17,7 @@ buffers (pinned H2D of the frame, D2H of the labels inside the timed region);
 `roofline` for the dominant kernel family (tcgen05 conv3d; tensor bound);
 `cpu_baseline` = the oracle port of the reference timed on this box's host
 cores on a bounded sample.  `--impl reference` times only that CPU path.
+`--segmenter dog` measures the plugin's second segmenter (configs[4]) with the same contract.
 """
 import argparse
 import json
@@ -370,6 +371,106 @@ def run_gpu(args, rank, local_rank, world):
     return 0
 
 
+# --------------------------------------------------------------------------------------
+# DoG blob segmenter arm (BASELINE.json configs[4]):  bench.py --segmenter dog
+# --------------------------------------------------------------------------------------
+def run_dog(args, rank, local_rank, world):
+    """One step = the DoG blob watershed (min_sigma 1, max_sigma 1.5, threshold 0.02) of one
+    synthetic 33x512x512 frame per rank.  Same JSON contract; `cpu_baseline` is the scipy + C
+    restatement (oracle/dog.py) on the same frame, one thread."""
+    import torch
+    import torch.distributed as dist
+    from iterseg_b200 import _lib, segmentation, synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    lib = _lib.load()
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    vol = synth.platelet_frame(FRAME, seed=rank)
+    frame = torch.from_numpy(vol).to(dev)
+    shape_p = tuple(s + 2 for s in FRAME)
+    labels = torch.zeros(shape_p, dtype=torch.int32, device=dev)
+    cfg = dict(min_sigma=1, max_sigma=1.5, threshold=0.02)
+    nvox = float(np.prod(FRAME))
+
+    def step():
+        labels.zero_()
+        return segmentation.dog_blob_segment_device(frame, labels, **cfg)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        mask, counts = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.isg_launch_count()
+    sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mask, counts = step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = int(lib.isg_launch_count() - launches0)
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    vol_pinned = torch.from_numpy(vol.copy()).pin_memory()
+    out_pinned = torch.zeros(shape_p, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        segmentation.dog_blob_watershed_for_chunks(vol_pinned.numpy(), out_pinned.numpy().view(np.uint32),
+                                                   CHUNK, MARGIN, **cfg)
+
+    for _ in range(2):
+        step_e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) / args.steps * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        hbm = float(peaks.get('hbm_gbs_sustained', peaks.get('hbm_gbs', 6650.0)))
+        ms = float(t.item())
+        c = counts.cpu().numpy()
+        line = {
+            'metric': 'voxels/sec DoG blob watershed', 'value': nvox * world / (ms * 1e-3), 'unit': 'voxels/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[4]: DoG blob watershed (min_sigma 1, max_sigma 1.5, threshold 0.02), one '
+                                   'synthetic platelet frame 33x512x512 per rank and step', 'frame': list(FRAME),
+                       'parallelism': f'frames x{world}' if world > 1 else 'single GPU',
+                       'objects': {'blobs': int(c[1]), 'labels': int(labels.max().item())}},
+            'e2e': {'value': nvox * world / (float(te.item()) * 1e-3), 'unit': 'voxels/s',
+                    'h2d_bytes_per_step': int(vol_pinned.numel() * 4) * world,
+                    'd2h_bytes_per_step': int(out_pinned.numel() * 4) * world},
+            'gpu_launches': launches, 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': 8.0 * nvox / (ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                         'frac': 8.0 * nvox / (ms * 1e-3) / 1e9 / hbm, 'traffic': None,
+                         'kernel': 'whole DoG stage (12 separable Gaussian passes, peaks, EDT, flood)',
+                         'peak_source': f'{peak_kind} hbm_gbs; 8 B per voxel compulsory (f32 in, i32 out)'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import dog
+            out = np.zeros(shape_p, np.int32)
+            t0 = time.perf_counter()
+            dog.dog_blob_watershed_for_chunks(vol, out, **cfg)
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {'value': nvox / dt, 'unit': 'voxels/s', 'cores': 1, 'kind': 'port',
+                                    'sample': 'one whole frame: scipy.ndimage Gaussians / EDT / label + C heap flood'}
+            line['identical_to_cpu_restatement'] = bool(np.array_equal(out, labels.cpu().numpy()))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def ctypes_double_array(n):
     import ctypes
     return (ctypes.c_double * n)()
@@ -382,6 +483,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--segmenter', default='affinity', choices=['affinity', 'dog'],
+                    help="'dog': the DoG blob watershed (BASELINE.json configs[4]) instead of the headline path")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -390,6 +493,8 @@ def main():
         return run_reference(args, rank)
     if args.warmup < 3:
         args.warmup = 3
+    if args.segmenter == 'dog':
+        return run_dog(args, rank, local_rank, world)
     return run_gpu(args, rank, local_rank, world)
 
 

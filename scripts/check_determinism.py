@@ -4,8 +4,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from iterseg_b200 import predict, synth, unet as U
-from oracle import unet_ref
-net = U.UNet(); net.load_state_dict(unet_ref.synth_state_dict(0)); net.cuda()
+net = U.UNet(); net.load_state_dict(synth.structured_state_dict(0)); net.cuda()
 vol = torch.from_numpy(synth.platelet_frame((12, 300, 300), seed=5)).cuda()
 a = predict.predict_frame_device(net, vol, (10, 256, 256), (1, 64, 64)).clone()
 b = predict.predict_frame_device(net, vol, (10, 256, 256), (1, 64, 64)).clone()

@@ -9,10 +9,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from iterseg_b200 import predict, synth, unet as U      # noqa: E402
-from oracle import unet_ref                             # noqa: E402
 
 net = U.UNet()
-net.load_state_dict(unet_ref.synth_state_dict(0))
+net.load_state_dict(synth.structured_state_dict(0))
 net.cuda()
 shape = (33, 512, 512)
 vol = torch.from_numpy(synth.platelet_frame(shape, seed=0)).cuda()

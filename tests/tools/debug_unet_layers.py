@@ -5,7 +5,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from iterseg_b200 import unet as U            # noqa: E402
 from oracle import unet_ref                   # noqa: E402

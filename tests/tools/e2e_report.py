@@ -1,7 +1,7 @@
 """End-to-end report on the GPU box: GPU pipeline vs the full CPU oracle pipeline."""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from iterseg_b200 import segmentation, synth, unet as U, predict, watershed as ws
 from oracle import unet_ref, post, metrics
