@@ -27,43 +27,9 @@
 #include <cub/cub.cuh>
 
 #include "flood_stage.h"
+#include "gauss.cuh"
 
 namespace isg {
-
-struct GaussD {
-    double w[12];
-    int r;
-};
-
-// one axis of scipy.ndimage.gaussian_filter (correlate1d, symmetric kernel), mode 0 = 'nearest',
-// 1 = 'reflect' (d c b a | a b c d | d c b a)
-template <int AXIS>
-__global__ void __launch_bounds__(256)
-dog_gauss_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t Z, uint32_t Y, uint32_t X,
-                 GaussD gw, int reflect) {
-    const uint64_t n = (uint64_t)Z * Y * X;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int len = (int)(AXIS == 0 ? Z : (AXIS == 1 ? Y : X));
-    const uint64_t step = AXIS == 0 ? (uint64_t)Y * X : (AXIS == 1 ? (uint64_t)X : 1ull);
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
-        const uint32_t x = (uint32_t)(v % X);
-        const uint64_t t = v / X;
-        const uint32_t y = (uint32_t)(t % Y), z = (uint32_t)(t / Y);
-        const int c = (int)(AXIS == 0 ? z : (AXIS == 1 ? y : x));
-        const uint64_t line0 = v - (uint64_t)c * step;
-        auto at = [&](int i) -> double {
-            if (reflect) {
-                while (i < 0 || i >= len) i = i < 0 ? -i - 1 : 2 * len - i - 1;
-            } else {
-                i = i < 0 ? 0 : (i >= len ? len - 1 : i);
-            }
-            return (double)__ldg(in + line0 + (uint64_t)i * step);
-        };
-        double acc = __dmul_rn((double)in[v], gw.w[0]);
-        for (int j = gw.r; j >= 1; --j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(at(c - j), at(c + j)), gw.w[j]));
-        out[v] = (float)acc;
-    }
-}
 
 __global__ void __launch_bounds__(256)
 pad_kernel(const float *__restrict__ vol, float *__restrict__ vp, uint32_t Z, uint32_t Y, uint32_t X) {
@@ -300,21 +266,14 @@ static void dog_carve(DogBuffers *b, Carver &cv, uint64_t np, int64_t max_seeds)
     flood_stage_workspace(&b->flood, cv, np, max_seeds);
 }
 
-template <int AXIS>
-static int gauss_pass(const float *in, float *out, uint32_t Z, uint32_t Y, uint32_t X, const GaussD &g, int reflect,
-                      cudaStream_t st) {
-    dog_gauss_kernel<AXIS><<<num_sms() * 8, 256, 0, st>>>(in, out, Z, Y, X, g, reflect);
-    ISG_LAUNCHED();
-    return ISG_OK;
-}
 // 3-axis Gaussian in -> out using tmp (in is preserved)
-static int gauss3(const float *in, float *tmp, float *out, uint32_t Z, uint32_t Y, uint32_t X, const GaussD &g,
+static int gauss3(const float *in, float *tmp, float *out, uint32_t Z, uint32_t Y, uint32_t X, const GaussW &g,
                   int reflect, cudaStream_t st) {
-    int rc = gauss_pass<0>(in, out, Z, Y, X, g, reflect, st);
+    int rc = gauss_axis(in, out, Z, Y, X, 0, g, reflect, nullptr, 0, 0, st);
     if (rc) return rc;
-    rc = gauss_pass<1>(out, tmp, Z, Y, X, g, reflect, st);
+    rc = gauss_axis(out, tmp, Z, Y, X, 1, g, reflect, nullptr, 0, 0, st);
     if (rc) return rc;
-    return gauss_pass<2>(tmp, out, Z, Y, X, g, reflect, st);
+    return gauss_axis(tmp, out, Z, Y, X, 2, g, reflect, nullptr, 0, 0, st);
 }
 
 }  // namespace isg
@@ -347,7 +306,7 @@ extern "C" int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int6
     ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE, "isg_dog_blob_segment: workspace too small (%zu < %zu)",
                 workspace_bytes, cv.off);
     const int grid = num_sms() * 8;
-    GaussD g[4];
+    GaussW g[4];
     for (int k = 0; k < 4; ++k) {
         g[k].r = prm->radius[k];
         for (int i = 0; i <= prm->radius[k]; ++i) g[k].w[i] = prm->weights[k][i];

@@ -1,0 +1,140 @@
+// One axis of scipy.ndimage.gaussian_filter (correlate1d with a symmetric kernel), tiled through
+// shared memory.  Arithmetic contract: double accumulation in scipy's
+// pairing order  x[c]*w[0] + sum_{j=r..1} (x[c-j] + x[c+j])*w[j],  no FMA contraction, float32
+// stored between passes; boundary 'nearest' (clamp) or 'reflect' (d c b a | a b c d | d c b a).
+// The volume is seen as (outer, L, inner): L = the filtered axis, inner = its element stride.
+#pragma once
+#include "common.cuh"
+
+namespace isg {
+
+struct GaussW {
+    double w[12];
+    int r;
+};
+
+static constexpr int GAUSS_TL = 32;      // outputs along the filtered axis per tile
+static constexpr int GAUSS_TI = 32;      // contiguous elements per tile row
+static constexpr int GAUSS_RMAX = 11;
+
+__device__ __forceinline__ int gauss_src_index(int i, int len, int reflect) {
+    if (reflect) {
+        while (i < 0 || i >= len) i = i < 0 ? -i - 1 : 2 * len - i - 1;
+        return i;
+    }
+    return i < 0 ? 0 : (i >= len ? len - 1 : i);
+}
+
+// Strided axes (inner >= 1 elements between neighbours along L, tiles of TI contiguous elements):
+// grid = (ceil(inner / TI), ceil(L / TL), outer), block = (TI, 8).
+// minmax (nullable): ordered-uint min / max of the outputs whose coordinate along the OUTERMOST
+// volume axis z lies in [mm_z0, mm_z1); z_of_outer / z_of_l say where z lives for this view.
+static __global__ void __launch_bounds__(GAUSS_TI * 8)
+gauss_tiled_kernel(const float *__restrict__ in, float *__restrict__ out, int L, int64_t inner, GaussW gw,
+                   int reflect, uint32_t *minmax, int z_is_l, int64_t outer_per_z, uint32_t mm_z0,
+                   uint32_t mm_z1) {
+    __shared__ float tile[GAUSS_TL + 2 * GAUSS_RMAX][GAUSS_TI + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t i0 = (int64_t)blockIdx.x * GAUSS_TI + tx;
+    const int l0 = blockIdx.y * GAUSS_TL;
+    const int64_t o = blockIdx.z;
+    const float *src = in + o * (int64_t)L * inner;
+    float *dst = out + o * (int64_t)L * inner;
+    const int r = gw.r;
+    for (int k = ty; k < GAUSS_TL + 2 * r; k += 8) {
+        const int l = gauss_src_index(l0 + k - r, L, reflect);
+        tile[k][tx] = i0 < inner ? __ldg(src + (int64_t)l * inner + i0) : 0.0f;
+    }
+    __syncthreads();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int k = ty; k < GAUSS_TL; k += 8) {
+        const int l = l0 + k;
+        if (l >= L || i0 >= inner) continue;
+        double acc = __dmul_rn((double)tile[k + r][tx], gw.w[0]);
+        for (int j = r; j >= 1; --j)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)tile[k + r - j][tx], (double)tile[k + r + j][tx]), gw.w[j]));
+        const float v = (float)acc;
+        dst[(int64_t)l * inner + i0] = v;
+        if (minmax) {
+            const uint32_t z = z_is_l ? (uint32_t)l : (uint32_t)(o / outer_per_z);
+            if (z >= mm_z0 && z < mm_z1) {
+                const uint32_t kk = f32_ord(v);
+                lo = min(lo, kk);
+                hi = max(hi, kk);
+            }
+        }
+    }
+    if (minmax) {
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (tx == 0) {
+            atomicMin(minmax + 0, lo);
+            atomicMax(minmax + 1, hi);
+        }
+    }
+}
+
+// The contiguous axis (x): one row segment of 256 outputs per block; grid = (ceil(X / 256),
+// min(rows, 65535)), rows walked with a grid stride.
+static __global__ void __launch_bounds__(256)
+gauss_row_kernel(const float *__restrict__ in, float *__restrict__ out, int X, int64_t rows, int64_t rows_per_z,
+                 GaussW gw, int reflect, uint32_t *minmax, uint32_t mm_z0, uint32_t mm_z1) {
+    __shared__ float seg[256 + 2 * GAUSS_RMAX];
+    const int x0 = blockIdx.x * 256;
+    const int r = gw.r;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const float *src = in + row * (int64_t)X;
+        __syncthreads();
+        for (int k = threadIdx.x; k < 256 + 2 * r; k += 256)
+            seg[k] = __ldg(src + gauss_src_index(x0 + k - r, X, reflect));
+        __syncthreads();
+        const int x = x0 + threadIdx.x;
+        if (x < X) {
+            const int c = threadIdx.x + r;
+            double acc = __dmul_rn((double)seg[c], gw.w[0]);
+            for (int j = r; j >= 1; --j)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)seg[c - j], (double)seg[c + j]), gw.w[j]));
+            const float v = (float)acc;
+            out[row * (int64_t)X + x] = v;
+            const uint32_t z = (uint32_t)(row / rows_per_z);
+            if (minmax && z >= mm_z0 && z < mm_z1) {
+                const uint32_t kk = f32_ord(v);
+                lo = min(lo, kk);
+                hi = max(hi, kk);
+            }
+        }
+    }
+    if (minmax) {
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(minmax + 0, lo);
+            atomicMax(minmax + 1, hi);
+        }
+    }
+}
+
+// axis: 0 = z, 1 = y, 2 = x of a (Z, Y, X) volume
+static inline int gauss_axis(const float *in, float *out, uint32_t Z, uint32_t Y, uint32_t X, int axis,
+                             const GaussW &gw, int reflect, uint32_t *minmax, uint32_t mm_z0, uint32_t mm_z1,
+                             cudaStream_t st) {
+    if (axis == 2) {
+        const int64_t rows = (int64_t)Z * Y;
+        dim3 grid((X + 255) / 256, (unsigned)(rows < 65535 ? rows : 65535));
+        gauss_row_kernel<<<grid, 256, 0, st>>>(in, out, (int)X, rows, (int64_t)Y, gw, reflect, minmax, mm_z0, mm_z1);
+        ISG_LAUNCHED();
+        return ISG_OK;
+    }
+    const int L = axis == 0 ? (int)Z : (int)Y;
+    const int64_t inner = axis == 0 ? (int64_t)Y * X : (int64_t)X;
+    const int64_t outer = axis == 0 ? 1 : (int64_t)Z;
+    ISG_REQUIRE(outer <= 65535, ISG_ERR_OVERFLOW, "gaussian: more than 65535 planes");
+    dim3 grid((unsigned)((inner + GAUSS_TI - 1) / GAUSS_TI), (unsigned)((L + GAUSS_TL - 1) / GAUSS_TL), (unsigned)outer);
+    gauss_tiled_kernel<<<grid, dim3(GAUSS_TI, 8), 0, st>>>(in, out, L, inner, gw, reflect, minmax, axis == 0 ? 1 : 0,
+                                                          1, mm_z0, mm_z1);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+}  // namespace isg

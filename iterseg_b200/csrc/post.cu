@@ -17,55 +17,9 @@
 #include <cub/cub.cuh>
 
 #include "flood_stage.h"
+#include "gauss.cuh"
 
 namespace isg {
-
-struct GaussW {
-    double w[12];
-    int r;
-};
-
-template <int AXIS>
-__global__ void __launch_bounds__(256)
-gauss_axis_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t Z, uint32_t Y,
-                  uint32_t X, GaussW gw, uint32_t *minmax /* nullable: ordered min, max */,
-                  uint32_t mm_z0 = 0, uint32_t mm_z1 = 0xFFFFFFFFu /* planes that count for min/max */) {
-    const uint64_t n = (uint64_t)Z * Y * X;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint32_t len = AXIS == 0 ? Z : (AXIS == 1 ? Y : X);
-    const uint64_t step = AXIS == 0 ? (uint64_t)Y * X : (AXIS == 1 ? (uint64_t)X : 1ull);
-    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
-        uint32_t x = (uint32_t)(v % X);
-        uint64_t t = v / X;
-        uint32_t y = (uint32_t)(t % Y);
-        uint32_t z = (uint32_t)(t / Y);
-        const uint32_t c = AXIS == 0 ? z : (AXIS == 1 ? y : x);
-        const uint64_t line0 = v - (uint64_t)c * step;
-        double acc = __dmul_rn((double)in[v], gw.w[0]);
-        for (int j = gw.r; j >= 1; --j) {
-            uint32_t a = c >= (uint32_t)j ? c - j : 0u;
-            uint32_t b = c + j < len ? c + j : len - 1;
-            double s = __dadd_rn((double)__ldg(in + line0 + a * step), (double)__ldg(in + line0 + b * step));
-            acc = __dadd_rn(acc, __dmul_rn(s, gw.w[j]));
-        }
-        float o = (float)acc;
-        out[v] = o;
-        if (minmax && z >= mm_z0 && z < mm_z1) {
-            uint32_t k = f32_ord(o);
-            lo = min(lo, k);
-            hi = max(hi, k);
-        }
-    }
-    if (minmax) {
-        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(minmax + 0, lo);
-            atomicMax(minmax + 1, hi);
-        }
-    }
-}
 
 // per-channel maximum of up to 3 planes (np.max(affinities, axis=(1,2,3)), watershed.py:195)
 __global__ void __launch_bounds__(256)
@@ -451,10 +405,10 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     const float *cent = feats + (uint64_t)prm->cent_ch * n;
     const float *smoothed_c = cent;
     if (prm->r1 > 0) {
-        gauss_axis_kernel<1><<<grid, 256, 0, st>>>(cent, b.tmp_a, Z, Y, X, g1, nullptr);
-        ISG_LAUNCHED();
-        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(b.tmp_a, b.tmp_b, Z, Y, X, g1, nullptr);
-        ISG_LAUNCHED();
+        int grc = gauss_axis(cent, b.tmp_a, Z, Y, X, 1, g1, 0, nullptr, 0, 0, st);
+        if (grc) return grc;
+        grc = gauss_axis(b.tmp_a, b.tmp_b, Z, Y, X, 2, g1, 0, nullptr, 0, 0, st);
+        if (grc) return grc;
         smoothed_c = b.tmp_b;
     }
     local_max_kernel<<<grid, 256, 0, st>>>(smoothed_c, Z, Y, X, prm->peak_thresh, b.cand_a,
@@ -478,20 +432,20 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     if (!prm->use_absolute_thresh) {
         const float *s = mraw;
         if (prm->r2 > 0) {
-            gauss_axis_kernel<0><<<grid, 256, 0, st>>>(mraw, b.tmp_a, Z, Y, X, g2, nullptr);
-            ISG_LAUNCHED();
-            gauss_axis_kernel<1><<<grid, 256, 0, st>>>(b.tmp_a, b.tmp_b, Z, Y, X, g2, nullptr);
-            ISG_LAUNCHED();
-            gauss_axis_kernel<2><<<grid, 256, 0, st>>>(b.tmp_b, b.tmp_a, Z, Y, X, g2, b.scal);
-            ISG_LAUNCHED();
+            int grc = gauss_axis(mraw, b.tmp_a, Z, Y, X, 0, g2, 0, nullptr, 0, 0, st);
+            if (grc) return grc;
+            grc = gauss_axis(b.tmp_a, b.tmp_b, Z, Y, X, 1, g2, 0, nullptr, 0, 0, st);
+            if (grc) return grc;
+            grc = gauss_axis(b.tmp_b, b.tmp_a, Z, Y, X, 2, g2, 0, b.scal, 0, 0xFFFFFFFFu, st);
+            if (grc) return grc;
             s = b.tmp_a;
         } else {
             // sigma = 0: min/max of the raw channel via an identity pass
             GaussW id;
             id.r = 0;
             id.w[0] = 1.0;
-            gauss_axis_kernel<2><<<grid, 256, 0, st>>>(mraw, b.tmp_a, Z, Y, X, id, b.scal);
-            ISG_LAUNCHED();
+            int grc = gauss_axis(mraw, b.tmp_a, Z, Y, X, 2, id, 0, b.scal, 0, 0xFFFFFFFFu, st);
+            if (grc) return grc;
             s = b.tmp_a;
         }
         hist_edges_kernel<<<1, 288, 0, st>>>(b.scal, b.edges);
@@ -627,18 +581,18 @@ extern "C" int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t
     uint32_t *mm = stage == 0 ? scal : nullptr;
     const float *s = tmp_a;
     if (prm->r2 > 0) {
-        gauss_axis_kernel<0><<<grid, 256, 0, st>>>(mraw, tmp_a, Z, Y, X, g2, nullptr);
-        ISG_LAUNCHED();
-        gauss_axis_kernel<1><<<grid, 256, 0, st>>>(tmp_a, tmp_b, Z, Y, X, g2, nullptr);
-        ISG_LAUNCHED();
-        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(tmp_b, tmp_a, Z, Y, X, g2, mm, oz0, oz1);
-        ISG_LAUNCHED();
+        int grc = gauss_axis(mraw, tmp_a, Z, Y, X, 0, g2, 0, nullptr, 0, 0, st);
+        if (grc) return grc;
+        grc = gauss_axis(tmp_a, tmp_b, Z, Y, X, 1, g2, 0, nullptr, 0, 0, st);
+        if (grc) return grc;
+        grc = gauss_axis(tmp_b, tmp_a, Z, Y, X, 2, g2, 0, mm, oz0, oz1, st);
+        if (grc) return grc;
     } else {
         GaussW id;
         id.r = 0;
         id.w[0] = 1.0;
-        gauss_axis_kernel<2><<<grid, 256, 0, st>>>(mraw, tmp_a, Z, Y, X, id, mm, oz0, oz1);
-        ISG_LAUNCHED();
+        int grc = gauss_axis(mraw, tmp_a, Z, Y, X, 2, id, 0, mm, oz0, oz1, st);
+        if (grc) return grc;
     }
     if (stage == 0) {
         ISG_REQUIRE(chan_max_out, ISG_ERR_ARG, "isg_slab_stats: chan_max_out is NULL");

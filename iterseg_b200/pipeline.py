@@ -67,6 +67,7 @@ class FramePipeline:
             slot['ev_post'].record(self.s_post)
         slot['busy'] = False
         slot['counts'] = counts
+        self.last_post_event = slot['ev_post']      # wait on this to read the labels (not on the next U-Net)
         self.n_out += 1
         self._reserve(False)
         return slot['labels'], counts

@@ -245,7 +245,8 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config):
         t_done, shape = pending.pop(0)
         lab, counts = pipe.collect()
         LAST_COUNTS['counts'] = counts
-        pipe.drain_to()
+        # only this frame's post stage has to be done: the next frame's U-Net keeps running
+        torch.cuda.current_stream(dev).wait_event(pipe.last_post_event)
         out = lab[1:-1, 1:-1, 1:-1].cpu().numpy().view(np.uint32)
         output_labels[t_done, ...] = out
         return t_done
