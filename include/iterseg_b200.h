@@ -150,7 +150,7 @@ int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t y, int64_t
                    float *minmax_io, float *chan_max_out, unsigned long long *hist_out,
                    void *workspace, size_t workspace_bytes, void *stream);
 int isg_otsu_from_hist(const unsigned long long *hist, const float *minmax, float *thr_out,
-                       void *stream);
+                       void *scratch /* >= 2048 bytes, device */, size_t scratch_bytes, void *stream);
 /* keys[0..n) ascending, in place (tmp: n uint64 of scratch + isg_sort_tmp_bytes(n) bytes) */
 size_t isg_sort_tmp_bytes(int64_t n);
 int isg_sort_keys_u64(unsigned long long *keys, int64_t n, void *tmp, size_t tmp_bytes, void *stream);

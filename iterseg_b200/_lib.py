@@ -41,7 +41,7 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     'isg_slab_stats': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _i32, _vp, _vp, _vp,
                               _vp, _sz, _vp]),
-    'isg_otsu_from_hist': (_i32, [_vp, _vp, _vp, _vp]),
+    'isg_otsu_from_hist': (_i32, [_vp, _vp, _vp, _vp, _sz, _vp]),
     'isg_sort_tmp_bytes': (_sz, [_i64]),
     'isg_sort_keys_u64': (_i32, [_vp, _i64, _vp, _sz, _vp]),
     'isg_relabel_by_keys': (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),

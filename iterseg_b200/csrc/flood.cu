@@ -369,7 +369,10 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     bq.complab = b.complab;
 
     const size_t smem_xl = (size_t)FLOOD_SMEM_ENTRIES * (sizeof(uint64_t) + sizeof(uint32_t));
-    static bool attr_set = false;
+    static bool attr_set_dev[16] = {false};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool &attr_set = attr_set_dev[cur_dev >= 0 && cur_dev < 16 ? cur_dev : 0];
     if (!attr_set) {
         ISG_CUDA(cudaFuncSetAttribute(flood_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem_xl));

@@ -620,20 +620,12 @@ extern "C" int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t
 }
 
 extern "C" int isg_otsu_from_hist(const unsigned long long *hist, const float *minmax, float *thr_out,
-                                  void *stream) {
-    ISG_REQUIRE(hist && minmax && thr_out, ISG_ERR_ARG, "isg_otsu_from_hist: null pointer");
+                                  void *scratch, size_t scratch_bytes, void *stream) {
+    ISG_REQUIRE(hist && minmax && thr_out && scratch, ISG_ERR_ARG, "isg_otsu_from_hist: null pointer");
+    ISG_REQUIRE(scratch_bytes >= 2048, ISG_ERR_WORKSPACE, "isg_otsu_from_hist: scratch must hold 2048 bytes");
     cudaStream_t st = (cudaStream_t)stream;
-    // scratch: ordered min/max + the 257 float32 bin edges live behind thr_out's caller? no: static per device
-    static thread_local uint32_t *scal = nullptr;
-    static thread_local float *edges = nullptr;
-    static thread_local int dev_of = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev_of != dev) {
-        ISG_CUDA(cudaMalloc(&scal, 64 * sizeof(uint32_t)));
-        ISG_CUDA(cudaMalloc(&edges, 320 * sizeof(float)));
-        dev_of = dev;
-    }
+    uint32_t *scal = reinterpret_cast<uint32_t *>(scratch);             // ordered min / max
+    float *edges = reinterpret_cast<float *>(scratch) + 64;             // 257 float32 bin edges
     float_to_ord_kernel<<<1, 32, 0, st>>>(minmax, scal, 2);
     ISG_LAUNCHED();
     hist_edges_kernel<<<1, 288, 0, st>>>(scal, edges);

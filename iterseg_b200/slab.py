@@ -206,9 +206,10 @@ class SlabWorker:
         dev = hist.device
         mm = torch.cat([gmin.reshape(1), gmax.reshape(1)]).to(dev, torch.float32).contiguous()
         thr = torch.zeros(1, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2048, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.isg_otsu_from_hist(hist.contiguous().data_ptr(), mm.data_ptr(), thr.data_ptr(),
-                                        _lib.stream_ptr())
+                                        scratch.data_ptr(), scratch.numel(), _lib.stream_ptr())
         _lib.check(rc, 'isg_otsu_from_hist')
         return float(thr.item())
 
