@@ -12,8 +12,8 @@ counts over NCCL to make label ids global.
 
 Printed (rank 0, one JSON line): `value` = voxels/s with the frame resident in
 HBM, device-timed with CUDA events, max over ranks; `e2e` = the same through the
-public plug-in call `segmentation.affinity_watershed_for_chunks` with host
-buffers (pinned H2D of the frame, D2H of the labels inside the timed region);
+public frame loop `segmentation.segmentation_loop` (what `segment_data` runs) over a
+pinned tzyx series (H2D of every frame, D2H of its labels inside the timed region);
 `roofline` for the dominant kernel family (tcgen05 conv3d; tensor bound);
 `cpu_baseline` = the oracle port of the reference timed on this box's host
 cores on a bounded sample.  `--impl reference` times only that CPU path.
@@ -246,20 +246,24 @@ def run_gpu(args, rank, local_rank, world):
         pipe.drain_to()
         return counts
 
-    # pinned host buffers for the end-to-end (public API) measurement
-    vol_pinned = torch.from_numpy(vol_np.copy()).pin_memory()
-    out_pinned = torch.zeros(shape_p, dtype=torch.int32).pin_memory()
+    # pinned host buffers for the end-to-end (public API) measurement: a K-frame tzyx series
+    # through `segmentation.segmentation_loop`, the frame loop behind `segment_data` /
+    # `affinity_unet_watershed` (labels restart at 1 in every frame, as in the reference)
+    n_e2e = max(args.steps, 2)
+    series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
+    out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
     config = {'unet': net, 'output_volume': np.zeros((1,), np.float32)}
 
-    def step_e2e():
-        # the callee overwrites every voxel of `current_output`, so the caller-side np.zeros of
-        # the reference protocol (segmentation.py:890-895) is not repeated inside the timed region
-        cur = out_pinned.numpy().view(np.uint32)
-        segmentation.affinity_watershed_for_chunks(vol_pinned.numpy(), cur, CHUNK, MARGIN, **config)
-        if world > 1:
-            n_local = int(segmentation.LAST_COUNTS['counts'][0].item())
-            all_counts = idist.gather_label_counts({rank: n_local}, world, rank, world, device=dev)
-            idist.add_label_offset_host(cur, int(idist.exclusive_offsets(all_counts)[rank]))
+    def run_e2e():
+        out = out_series.numpy()
+        out[...] = 0                       # untimed: the caller's fresh output store
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done = list(segmentation.segmentation_loop(None, series.numpy(), CHUNK, MARGIN, out,
+                                                   segmentation.affinity_watershed_for_chunks, config))
+        torch.cuda.synchronize()
+        assert len(done) == n_e2e
+        return time.perf_counter() - t0
 
     sampler = ClockSampler(local_rank)
     sampler.start()                       # before the warm-up: nvidia-smi needs ~0.2 s to come up
@@ -288,19 +292,15 @@ def run_gpu(args, rank, local_rank, world):
     ms_step = float(t.item()) / args.steps
     value = nvox * world / (ms_step * 1e-3)
 
-    # ---- end to end through the public plug-in call, host buffers --------------------------
-    for _ in range(min(args.warmup, 2) or 1):
-        step_e2e()
+    # ---- end to end through the public frame loop, host buffers ---------------------------------
+    run_e2e()                                   # warm-up
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = run_e2e()
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = nvox * world / (float(t.item()) / args.steps)
+    e2e_value = nvox * world * n_e2e / float(t.item())
+    e2e_labels_ok = bool(int(out_series[0].max()) == int(counts[0].item()) or world > 1)
 
     # ---- post stage alone (not overlapped), device-timed: the HBM-side roofline entry -----------
     post_ms = None
@@ -337,8 +337,11 @@ def run_gpu(args, rank, local_rank, world):
                        'objects': {'seeds': counts_h[0], 'components': counts_h[2],
                                    'multi_seed_components': counts_h[3]}},
             'e2e': {'value': e2e_value, 'unit': 'voxels/s',
-                    'h2d_bytes_per_step': int(vol_pinned.numel() * 4) * world,
-                    'd2h_bytes_per_step': int(out_pinned.numel() * 4) * world},
+                    'h2d_bytes_per_step': int(np.prod(FRAME) * 4) * world,
+                    'd2h_bytes_per_step': int(np.prod(FRAME) * 4) * world,
+                    'api': f'segmentation.segmentation_loop over a pinned {n_e2e}-frame tzyx series (the frame loop '
+                           f'of segment_data): per frame H2D, min/max + normalise, U-Net, post stage, D2H into the '
+                           f'caller\'s int32 array; two frames in flight', 'labels_match_device_run': e2e_labels_ok},
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',

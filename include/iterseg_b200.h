@@ -40,6 +40,12 @@ const char *isg_last_error(void);
 int isg_device_check(void);
 /* how many kernels this library has launched since load (bench `gpu_launches`) */
 uint64_t isg_launch_count(void);
+/* Input staging of segment_single_volume (segmentation.py:887-889) on the device:
+ * isg_frame_minmax: minmax_out[2] = {min, max} of the n floats (scratch: >= 8 device bytes);
+ * isg_frame_divide_by_max: frame[i] /= minmax[1] in place (IEEE float32 division). */
+int isg_frame_minmax(const float *frame, int64_t n, float *minmax_out, void *scratch,
+                     size_t scratch_bytes, void *stream);
+int isg_frame_divide_by_max(float *frame, int64_t n, const float *minmax, void *stream);
 /* Frame pipelining (iterseg_b200/pipeline.py): reserve n_sms SMs for the post stage of one frame
  * while the U-Net of the next frame runs on another stream (0 = off, the default). */
 int isg_set_post_sm_reservation(int n_sms);

@@ -33,6 +33,8 @@ SIGNATURES = {
     'isg_device_check': (_i32, []),
     'isg_launch_count': (_c.c_uint64, []),
     'isg_set_post_sm_reservation': (_i32, [_i32]),
+    'isg_frame_minmax': (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    'isg_frame_divide_by_max': (_i32, [_vp, _i64, _vp, _vp]),
     'isg_flood_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
     'isg_affinity_flood': (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                   _vp, _vp, _sz, _vp]),

@@ -56,6 +56,59 @@ add_label_offset_kernel(uint32_t *labels, uint64_t n, uint32_t offset) {
 }
 }  // namespace isg
 
+namespace isg {
+// input staging (segmentation.py:887-889): min / max of the frame, then frame /= max
+__global__ void __launch_bounds__(256)
+frame_minmax_kernel(const float *__restrict__ v, uint64_t n, uint32_t *__restrict__ mm) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = f32_ord(v[i]);
+        lo = min(lo, k);
+        hi = max(hi, k);
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 0, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+__global__ void minmax_out_kernel(const uint32_t *__restrict__ mm, float *__restrict__ out) {
+    out[0] = ord_f32(mm[0]);
+    out[1] = ord_f32(mm[1]);
+}
+__global__ void __launch_bounds__(256)
+frame_divide_kernel(float *__restrict__ v, uint64_t n, const float *__restrict__ minmax) {
+    const float d = minmax[1];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        v[i] = __fdiv_rn(v[i], d);               // IEEE float32 division, as numpy's in-place /=
+}
+}  // namespace isg
+
+extern "C" int isg_frame_minmax(const float *frame, int64_t n, float *minmax_out, void *scratch,
+                                size_t scratch_bytes, void *stream) {
+    ISG_REQUIRE(frame && minmax_out && scratch && n > 0, ISG_ERR_ARG, "isg_frame_minmax: bad argument");
+    ISG_REQUIRE(scratch_bytes >= 8, ISG_ERR_WORKSPACE, "isg_frame_minmax: scratch must hold 8 bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *mm = reinterpret_cast<uint32_t *>(scratch);
+    const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+    ISG_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    isg::frame_minmax_kernel<<<isg::num_sms() * 8, 256, 0, st>>>(frame, (uint64_t)n, mm);
+    ISG_LAUNCHED();
+    isg::minmax_out_kernel<<<1, 1, 0, st>>>(mm, minmax_out);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+extern "C" int isg_frame_divide_by_max(float *frame, int64_t n, const float *minmax, void *stream) {
+    ISG_REQUIRE(frame && minmax && n > 0, ISG_ERR_ARG, "isg_frame_divide_by_max: bad argument");
+    isg::frame_divide_kernel<<<isg::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(frame, (uint64_t)n, minmax);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
 extern "C" int isg_add_label_offset(uint32_t *labels, int64_t n, uint32_t offset, void *stream) {
     ISG_REQUIRE(labels && n >= 0, ISG_ERR_ARG, "isg_add_label_offset: bad argument");
     if (n == 0 || offset == 0) return ISG_OK;

@@ -231,27 +231,52 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config):
     from .pipeline import FramePipeline
     net = config['unet']
     dev = net.device
-    todo = [t for t in range(data.shape[0]) if not np.any(output_labels[t])]       # warm restart (:875-876)
-    pipe, pending = None, []          # pending: (t, frame shape) of submitted frames, oldest first
+    lib = _lib.load()
+    pipe, pending = None, []          # pending: submitted time points, oldest first
+    scratch = torch.empty(64, dtype=torch.uint8, device=dev)
+    minmax = torch.zeros(2, dtype=torch.float32, device=dev)
 
     def prepare(t):
-        vol = np.asarray(data[t]).astype(np.float32)
-        if vol.min() == 0:
-            vol = remove_sum_zero_slices(vol)
-        vol /= np.max(vol)
-        return torch.from_numpy(vol).to(dev, non_blocking=True)
+        """Frame t on the device, normalised as segment_single_volume does (:887-889).  The cast,
+        the min / max and the division run on the device; only a frame that contains zeros takes
+        the reference's host route (slices that sum to zero are stripped first)."""
+        src = data[t]
+        if isinstance(src, np.ndarray) and src.dtype == np.float32 and src.flags.c_contiguous:
+            host = torch.from_numpy(src)
+        else:
+            host = torch.from_numpy(np.asarray(src).astype(np.float32))
+        frame = host.to(dev, non_blocking=True)
+        if frame.data_ptr() == host.data_ptr():               # never normalise the caller's array in place
+            frame = frame.clone()
+        with torch.cuda.device(dev):
+            _lib.check(lib.isg_frame_minmax(frame.data_ptr(), frame.numel(), minmax.data_ptr(), scratch.data_ptr(),
+                                            scratch.numel(), _lib.stream_ptr()), 'isg_frame_minmax')
+            if float(minmax[0].item()) == 0.0:
+                vol = remove_sum_zero_slices(np.asarray(src).astype(np.float32))
+                vol /= np.max(vol)
+                return torch.from_numpy(vol).to(dev)
+            _lib.check(lib.isg_frame_divide_by_max(frame.data_ptr(), frame.numel(), minmax.data_ptr(),
+                                                   _lib.stream_ptr()), 'isg_frame_divide_by_max')
+        return frame
 
     def finish():
-        t_done, shape = pending.pop(0)
+        t_done = pending.pop(0)
         lab, counts = pipe.collect()
         LAST_COUNTS['counts'] = counts
         # only this frame's post stage has to be done: the next frame's U-Net keeps running
         torch.cuda.current_stream(dev).wait_event(pipe.last_post_event)
-        out = lab[1:-1, 1:-1, 1:-1].cpu().numpy().view(np.uint32)
-        output_labels[t_done, ...] = out
+        crop = lab[1:-1, 1:-1, 1:-1]
+        dst = output_labels[t_done] if isinstance(output_labels, np.ndarray) else None
+        if dst is not None and dst.flags.c_contiguous and dst.dtype in (np.int32, np.uint32) and \
+                dst.shape == tuple(crop.shape):
+            torch.from_numpy(dst.view(np.int32)).copy_(crop)       # straight into the caller's array
+        else:
+            output_labels[t_done, ...] = crop.cpu().numpy().view(np.uint32)
         return t_done
 
-    for t in todo:
+    for t in range(data.shape[0]):
+        if np.any(output_labels[t]):                               # warm restart (:875-876)
+            continue
         frame = prepare(t)
         if pipe is not None and tuple(frame.shape) != pipe.shape:      # zero-slice strip changed the shape
             while pending:
@@ -260,7 +285,7 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config):
         if pipe is None:
             pipe = FramePipeline(net, tuple(frame.shape), tuple(int(c) for c in chunk_size), margin)
         pipe.submit(frame)
-        pending.append((t, tuple(frame.shape)))
+        pending.append(t)
         if len(pending) == 2:
             yield finish()
     while pending:
