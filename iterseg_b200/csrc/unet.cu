@@ -389,6 +389,8 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     auto vox = [&](int l) { return (size_t)p->D[l] * p->H[l] * p->W[l]; };
     ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
     // ---- c0.conv0 (CUDA cores, straight from the frame) ----
+    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_in_w, pk + L.w[0], sizeof(float) * 27 * 32, 0, cudaMemcpyDeviceToDevice, st));
+    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_out_w, pk + L.w[17], sizeof(float) * 27 * 25, 0, cudaMemcpyDeviceToDevice, st));
     conv_in_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(frame, p->Z, p->Y, p->X, p->starts,
                                                      reinterpret_cast<const float *>(pk + L.w[0]),
                                                      p->raw[0], p->stats[0], p->D[0], p->H[0], p->W[0]);

@@ -209,6 +209,12 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], unsigned lon
 // c0.conv0: Cin = 1 -> 32, fp32 CUDA cores, reads the chunk straight out of the frame
 // (zero padding at the CHUNK border, as the reference pads the sliced chunk).
 // starts: [N][3] chunk origins.  grid = (blocks, N), block 256.
+// The two tiny convolutions keep their weights in constant memory: after unrolling every weight is
+// an immediate constant-bank operand of its FFMA (all lanes use the same weight at the same time), so
+// no load instruction and no register is spent on it.  Uploaded per forward (unet.cu).
+__constant__ float c_conv_in_w[27 * 32];
+__constant__ float c_conv_out_w[27 * 25];
+
 // Each thread computes CONV_VX consecutive x voxels, so that a weight read from shared memory
 // (one LDS.128 = 4 channels) feeds CONV_VX FMAs per channel instead of one.
 static constexpr int CONV_VX = 4;
@@ -217,9 +223,6 @@ __global__ void __launch_bounds__(256)
 conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *__restrict__ starts,
                const float *__restrict__ wgt /* [27][32] */, __half *__restrict__ raw,
                unsigned long long *__restrict__ stats, int D, int H, int W) {
-    __shared__ __align__(16) float w_s[27 * 32];
-    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) w_s[i] = wgt[i];
-    __syncthreads();
     const int n = blockIdx.y;
     const int z0 = starts[n * 3 + 0], y0 = starts[n * 3 + 1], x0 = starts[n * 3 + 2];
     const size_t vox = (size_t)D * H * W;
@@ -252,17 +255,11 @@ conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *
             }
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const float4 *wv = reinterpret_cast<const float4 *>(w_s + (zy * 3 + dx) * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 k4 = wv[q];
+                for (int c = 0; c < 32; ++c) {
+                    const float k = c_conv_in_w[(zy * 3 + dx) * 32 + c];
 #pragma unroll
-                    for (int j = 0; j < CONV_VX; ++j) {
-                        acc[j][q * 4 + 0] = fmaf(in[j + dx], k4.x, acc[j][q * 4 + 0]);
-                        acc[j][q * 4 + 1] = fmaf(in[j + dx], k4.y, acc[j][q * 4 + 1]);
-                        acc[j][q * 4 + 2] = fmaf(in[j + dx], k4.z, acc[j][q * 4 + 2]);
-                        acc[j][q * 4 + 3] = fmaf(in[j + dx], k4.w, acc[j][q * 4 + 3]);
-                    }
+                    for (int j = 0; j < CONV_VX; ++j) acc[j][c] = fmaf(in[j + dx], k, acc[j][c]);
                 }
             }
         }
@@ -296,11 +293,9 @@ conv_out_kernel(const float *__restrict__ raw8, const unsigned long long *__rest
                 const float *__restrict__ gamma8, const float *__restrict__ beta8,
                 const float *__restrict__ wgt /* [27][5 in][5 out] */, float *__restrict__ raw9,
                 unsigned long long *__restrict__ stats9, int D, int H, int W) {
-    __shared__ float w_s[27 * 25];
     __shared__ float sc[5], sh[5];
     const int n = blockIdx.y;
     const size_t vox = (size_t)D * H * W;
-    for (int i = threadIdx.x; i < 27 * 25; i += blockDim.x) w_s[i] = wgt[i];
     if (threadIdx.x < 5)
         bn_coeffs(stats8 + ((size_t)n * 16 + threadIdx.x) * 2, gamma8[threadIdx.x], beta8[threadIdx.x],
                   1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
@@ -346,7 +341,7 @@ conv_out_kernel(const float *__restrict__ raw8, const unsigned long long *__rest
                     for (int j = 0; j < CONV_VX; ++j) {
                         const int dy = r - j;                   // this row is tap dy of output row h + j
                         if (dy < 0 || dy > 2) continue;
-                        const float *k = w_s + ((dz * 3 + dy) * 3 + dx) * 25;
+                        const float *k = c_conv_out_w + ((dz * 3 + dy) * 3 + dx) * 25;
 #pragma unroll
                         for (int ci = 0; ci < 5; ++ci)
 #pragma unroll
