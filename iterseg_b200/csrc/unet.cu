@@ -132,6 +132,7 @@ struct isg_unet_plan {
     float *raw8, *raw9;
     unsigned long long *stats[18];
     unsigned long long *stats_all;
+    unsigned int *sched[18];
     size_t stats_bytes;
     isg::TcLayer tc[18];
     int base_off_mode;
@@ -185,14 +186,17 @@ static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
     p->raw9 = cv.take<float>(vox(0) * 8);
     size_t floats = 0;
     for (int i = 0; i < 18; ++i) floats += (size_t)N * cout_pad(i) * 2;
-    p->stats_all = cv.take<unsigned long long>(floats);
-    p->stats_bytes = floats * sizeof(unsigned long long);
+    // + one 8-byte slot per conv for the group counter of its dynamic scheduler (unet_conv.cuh);
+    // the memset that clears the statistics at the start of a forward pass clears these too
+    p->stats_all = cv.take<unsigned long long>(floats + 18);
+    p->stats_bytes = (floats + 18) * sizeof(unsigned long long);
     if (p->stats_all) {
         unsigned long long *s = p->stats_all;
         for (int i = 0; i < 18; ++i) {
             p->stats[i] = s;
             s += (size_t)N * cout_pad(i) * 2;
         }
+        for (int i = 0; i < 18; ++i) p->sched[i] = reinterpret_cast<unsigned int *>(s + i);
     }
     return cv.off;
 }
@@ -298,6 +302,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     { const char *dbg = getenv("ISG_CONV_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
     g.out = out;
     g.stats = p->stats[i];
+    g.sched = p->sched[i];
     t.smem = conv_smem_bytes(g);
     t.grid = g.n_groups < num_sms() ? g.n_groups : num_sms();
     if (!make_act_map(&t.tmA0, src0, c0, g.W, g.H, g.D, g.N, cblk, g.P, g.Ht)) return false;

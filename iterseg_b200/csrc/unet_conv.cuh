@@ -32,8 +32,15 @@
 //      27 -> 9 MMAs per channel step.
 //   Plane slots and accumulators are released one by one at their last use, so the loads of
 //   the next channel block / group and the epilogue overlap the MMAs.
-// Warp roles: 0 = A producer, 3 = B producer, 1 = MMA issuer (one thread),
-//             2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> global + statistics).
+//   SCHEDULER: a CTA starts with group blockIdx.x and then takes the next free group from a global
+//      counter (atomicAdd by the A producer, one group ahead of its loads), published to the
+//      other roles through a 4-deep shared-memory ring guarded by mbarriers.  The post stage of the
+//      previous frame runs beside the U-Net on a second stream and its long flood blocks
+//      own whole SMs (227 KB of shared memory) for milliseconds: with a static grid-stride
+//      partition the conv CTA that cannot be placed starts late and the whole launch waits for
+//      its share; with the counter the placed CTAs simply take the work.
+// Warp roles: 0 = A producer + scheduler, 3 = B producer, 1,2 = MMA issuers (one elected lane each;
+//             2 also allocates TMEM), 4..7 = epilogue (TMEM -> regs -> global + statistics).
 #pragma once
 #include <cuda.h>
 
@@ -66,6 +73,8 @@ struct ConvGeom {
     void *out;
     unsigned long long *stats;   // [N][cout][2] (sum, sum of squares) as 2^-24 fixed point:
                                  // integer atomics are order-independent -> reproducible
+    unsigned int *sched;         // group counter of this launch (zeroed by the caller): groups beyond the
+                                 // first one of a CTA are handed out dynamically, see "scheduler" below
 };
 
 static constexpr int CONV_THREADS = 256;
@@ -74,6 +83,9 @@ static constexpr int CONV_SLACK = 4096;      // garbage rows the last taps of in
 static constexpr int CONV_MAX_T = 10;
 static constexpr int CONV_MAX_B_STAGES = 24;
 static constexpr int CONV_BAR_BYTES = 1024;
+static constexpr int CONV_SCHED_SLOTS = 4;   // ring of published group indices
+static_assert((66 + 2 * CONV_MAX_B_STAGES + 2 * CONV_SCHED_SLOTS) * 8 + CONV_SCHED_SLOTS * 4 <= CONV_BAR_BYTES,
+              "barrier block too small");
 
 __host__ __device__ inline size_t conv_smem_bytes(const ConvGeom &g) {
     return 1024 /* alignment */ + (size_t)(g.T + 2) * g.plane_bytes +
@@ -101,6 +113,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t *acc_full = bars + 24, *acc_empty = bars + 44;            // [nsets * T] <= 20 each
     uint64_t *b_full = bars + 64, *b_empty = bars + 64 + CONV_MAX_B_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 64 + 2 * CONV_MAX_B_STAGES);
+    uint64_t *sched_full = bars + 66 + 2 * CONV_MAX_B_STAGES, *sched_empty = sched_full + CONV_SCHED_SLOTS;
+    volatile int *sched_grp = reinterpret_cast<volatile int *>(sched_empty + CONV_SCHED_SLOTS);
     float *stat_t = reinterpret_cast<float *>(tail + CONV_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
@@ -125,6 +139,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(&b_full[i], 1);
             mbar_init(&b_empty[i], 2);
         }
+        for (int i = 0; i < CONV_SCHED_SLOTS; ++i) {
+            mbar_init(&sched_full[i], 1);
+            // readers: 2 MMA warps + 4 epilogue warps (+ the B producer when it streams weights)
+            mbar_init(&sched_empty[i], g.b_resident ? 6 : 7);
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -148,10 +167,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     };
 
     if (warp == 0) {
-        // ===================== A producer =====================
+        // ===================== A producer + scheduler =====================
         if (lane == 0) {
             uint32_t ph = 0;                                  // per plane slot: uses so far (parity)
-            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+            uint32_t sidx = 0;
+            int grp = blockIdx.x;
+            for (;;) {
+                const uint32_t slot = sidx % CONV_SCHED_SLOTS, sph = (sidx / CONV_SCHED_SLOTS) & 1u;
+                mbar_wait(&sched_empty[slot], sph ^ 1u);
+                sched_grp[slot] = grp;                        // >= n_groups: the stop mark
+                mbar_arrive(&sched_full[slot]);               // release: readers see the store
+                ++sidx;
+                if (grp >= g.n_groups) break;
+                // the following group, requested now and needed after this group's loads
+                const int next = (int)gridDim.x + (int)atomicAdd(g.sched, 1u);
                 int wb, hb, d0, n, tg;
                 decode(grp, wb, hb, d0, n, tg);
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -167,6 +196,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                     ph ^= (1u << (tg + 2)) - 1u;
                 }
+                grp = next;
             }
         }
     } else if (warp == 3) {
@@ -181,9 +211,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                     bg * G);
                     }
             } else {
-                uint32_t it = 0;
+                uint32_t it = 0, sidx = 0;
                 const uint32_t nb = (uint32_t)g.n_b_stages;
-                for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+                for (;; ++sidx) {
+                    const uint32_t slot = sidx % CONV_SCHED_SLOTS;
+                    mbar_wait(&sched_full[slot], (sidx / CONV_SCHED_SLOTS) & 1u);
+                    const int grp = sched_grp[slot];
+                    mbar_arrive(&sched_empty[slot]);
+                    if (grp >= g.n_groups) break;
                     for (int kb = 0; kb < nkb; ++kb) {
                         for (int bg = 0; bg < NBG; ++bg, ++it) {
                             const uint32_t s = it % nb, ph = (it / nb) & 1u;
@@ -227,10 +262,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t b_stage_units = (uint32_t)g.b_stage_bytes >> 4;
             const uint32_t acc_cols = (uint32_t)g.acc_cols;
             const int T = g.T, D = g.D, nsets = g.nsets, n_groups = g.n_groups, b_resident = g.b_resident;
-            const int gstride = (int)gridDim.x;
             const int dgroups = g.dgroups, tiles_hw = g.tiles_h * g.tiles_w;
             uint32_t gcount = 0, bs = 0, bph = 0;                  // weight ring position / parity
-            for (int grp = blockIdx.x; grp < n_groups; grp += gstride, ++gcount) {
+            for (;; ++gcount) {
+                const uint32_t slot = gcount % CONV_SCHED_SLOTS;
+                mbar_wait(&sched_full[slot], (gcount / CONV_SCHED_SLOTS) & 1u);
+                const int grp = sched_grp[slot];
+                __syncwarp();                                  // every lane has read the slot
+                if (leader) mbar_arrive(&sched_empty[slot]);
+                if (grp >= n_groups) break;
                 const int dg = (grp / tiles_hw) % dgroups;
                 const int d0 = dg * T;
                 const int tg = D - d0 < T ? D - d0 : T;
@@ -356,7 +396,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         };
         uint32_t acc_ph = 0, gcount = 0;
-        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++gcount) {
+        for (;; ++gcount) {
+          const uint32_t slot = gcount % CONV_SCHED_SLOTS;
+          mbar_wait(&sched_full[slot], (gcount / CONV_SCHED_SLOTS) & 1u);
+          const int grp = sched_grp[slot];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sched_empty[slot]);
+          if (grp >= g.n_groups) break;
           int wb, hb, d0, n, tg;
           decode(grp, wb, hb, d0, n, tg);
           const int a0 = g.nsets == 2 ? (int)(gcount & 1u) * g.T : 0;
