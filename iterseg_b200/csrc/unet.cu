@@ -15,6 +15,7 @@
 
 #include "unet_conv.cuh"
 #include "unet_elem.cuh"
+#include "unet_thin.cuh"
 
 namespace isg {
 
@@ -371,6 +372,40 @@ static int launch_tc(const TcLayer &t, cudaStream_t st) {
     }
 }
 
+static int launch_thin(const ThinArgs &a, cudaStream_t st) {
+    constexpr size_t smem = thin_smem_bytes();
+    static int per_sm[16] = {0};
+    int dev = 0;
+    ISG_CUDA(cudaGetDevice(&dev));
+    if (per_sm[dev & 15] == 0) {
+        ISG_CUDA(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        ISG_CUDA(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        // resident CTAs per SM from the kernel's own footprint: shared memory (+1 KB the hardware
+        // reserves per CTA), registers, and 32 of the SM's 512 TMEM columns each
+        cudaFuncAttributes fa;
+        ISG_CUDA(cudaFuncGetAttributes(&fa, conv_in_tc_kernel));
+        int smem_sm = 0, regs_sm = 0;
+        ISG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        ISG_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+        int occ = (int)((size_t)smem_sm / (smem + 1024 + fa.sharedSizeBytes));
+        const int by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * THIN_THREADS);
+        if (by_regs < occ) occ = by_regs;
+        per_sm[dev & 15] = occ < 1 ? 1 : (occ > 16 ? 16 : occ);
+    }
+    const long long units = (long long)a.N * a.D * ((a.H + 3) / 4) * ((a.W + 31) / 32);
+    if (units >= (1ll << 31)) {
+        set_error("thin conv: %lld units exceed the 32-bit unit index", units);
+        return ISG_ERR_ARG;
+    }
+    long long grid = (long long)num_sms() * per_sm[dev & 15];
+    if (grid > units) grid = units;
+    conv_in_tc_kernel<<<(unsigned)grid, THIN_THREADS, smem, st>>>(a);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
 static inline dim3 egrid(size_t work, int N) {
     size_t b = (work + 255) / 256;
     const size_t cap = (size_t)num_sms() * 16;
@@ -393,13 +428,16 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     auto B = [&](int i) { return reinterpret_cast<const float *>(pk + L.beta[i]); };
     auto vox = [&](int l) { return (size_t)p->D[l] * p->H[l] * p->W[l]; };
     ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
-    // ---- c0.conv0 (CUDA cores, straight from the frame) ----
-    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_in_w, pk + L.w[0], sizeof(float) * 27 * 32, 0, cudaMemcpyDeviceToDevice, st));
-    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_out_w, pk + L.w[17], sizeof(float) * 27 * 25, 0, cudaMemcpyDeviceToDevice, st));
-    conv_in_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(frame, p->Z, p->Y, p->X, p->starts,
-                                                     reinterpret_cast<const float *>(pk + L.w[0]),
-                                                     p->raw[0], p->stats[0], p->D[0], p->H[0], p->W[0]);
-    ISG_LAUNCHED();
+    // ---- c0.conv0 (1 -> 32, im2col on tensor cores, straight from the frame) ----
+    {
+        ThinArgs a{};
+        a.src = frame; a.starts = p->starts; a.Y = p->Y; a.X = p->X;
+        a.wgt = reinterpret_cast<const float *>(pk + L.w[0]);
+        a.out = p->raw[0]; a.stats = p->stats[0];
+        a.N = N; a.D = p->D[0]; a.H = p->H[0]; a.W = p->W[0];
+        int rc = launch_thin(a, st);
+        if (rc) return rc;
+    }
     if (stop == 0) return ISG_OK;
     static const int CH[5] = {32, 64, 128, 256, 256};
     // ---- encoder ----
@@ -462,6 +500,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         }
     }
     // ---- c8_0.conv1 (5 -> 5) + BN + sigmoid + placement ----
+    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_out_w, pk + L.w[17], sizeof(float) * 27 * 25, 0, cudaMemcpyDeviceToDevice, st));
     conv_out_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(p->raw8, p->stats[16], G(16), B(16),
                                                       reinterpret_cast<const float *>(pk + L.w[17]),
                                                       p->raw9, p->stats[17], p->D[0], p->H[0], p->W[0]);

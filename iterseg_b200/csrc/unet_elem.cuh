@@ -1,7 +1,7 @@
 // Memory-bound companions of the tensor-core convolutions (all channels-last fp16,
 // fp32 math): train-mode BatchNorm apply + ReLU, fused with max-pool (encoder) or
-// with the depthwise transposed convolution + crop (decoder); the two CUDA-core
-// convolutions that are too thin for tensor cores (Cin = 1 and 5 -> 5); the final
+// with the depthwise transposed convolution + crop (decoder); the 5 -> 5 CUDA-core
+// convolution (c0.conv0, 1 -> 32, is an im2col tensor-core kernel: unet_thin.cuh); the final
 // BatchNorm + sigmoid + crop-and-place.
 //
 // Reference: ConvModule.forward (src/iterseg/unet.py:91-106), MaxPool3d layers
@@ -206,84 +206,13 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], unsigned lon
     __syncthreads();
 }
 
-// c0.conv0: Cin = 1 -> 32, fp32 CUDA cores, reads the chunk straight out of the frame
-// (zero padding at the CHUNK border, as the reference pads the sliced chunk).
-// starts: [N][3] chunk origins.  grid = (blocks, N), block 256.
-// The two tiny convolutions keep their weights in constant memory: after unrolling every weight is
-// an immediate constant-bank operand of its FFMA (all lanes use the same weight at the same time), so
-// no load instruction and no register is spent on it.  Uploaded per forward (unet.cu).
-__constant__ float c_conv_in_w[27 * 32];
+// c8_0.conv1 keeps its weights in constant memory: after unrolling every weight is an immediate
+// constant-bank operand of its FFMA (all lanes use the same weight at the same time), so no load
+// instruction and no register is spent on it.  Uploaded per forward (unet.cu).
 __constant__ float c_conv_out_w[27 * 25];
 
-// Each thread computes CONV_VX consecutive x voxels, so that a weight read from shared memory
-// (one LDS.128 = 4 channels) feeds CONV_VX FMAs per channel instead of one.
+// Each thread computes CONV_VX voxels, so that a weight feeds CONV_VX FMAs per channel.
 static constexpr int CONV_VX = 4;
-
-__global__ void __launch_bounds__(256)
-conv_in_kernel(const float *__restrict__ frame, int Z, int Y, int X, const int *__restrict__ starts,
-               const float *__restrict__ wgt /* [27][32] */, __half *__restrict__ raw,
-               unsigned long long *__restrict__ stats, int D, int H, int W) {
-    const int n = blockIdx.y;
-    const int z0 = starts[n * 3 + 0], y0 = starts[n * 3 + 1], x0 = starts[n * 3 + 2];
-    const size_t vox = (size_t)D * H * W;
-    const int wq = (W + CONV_VX - 1) / CONV_VX;
-    const size_t units = (size_t)D * H * wq;
-    float ssum[32], ssq[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.0f;
-    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units;
-         u += (size_t)gridDim.x * blockDim.x) {
-        const int w = (int)(u % wq) * CONV_VX;
-        const size_t t = u / wq;
-        const int h = (int)(t % H);
-        const int d = (int)(t / H);
-        float acc[CONV_VX][32];
-#pragma unroll
-        for (int j = 0; j < CONV_VX; ++j)
-#pragma unroll
-            for (int c = 0; c < 32; ++c) acc[j][c] = 0.0f;
-#pragma unroll
-        for (int zy = 0; zy < 9; ++zy) {
-            const int dd = d + zy / 3 - 1, hh = h + zy % 3 - 1;
-            float in[CONV_VX + 2];
-            const bool row_ok = dd >= 0 && dd < D && hh >= 0 && hh < H;
-            const float *row = frame + ((size_t)(z0 + (row_ok ? dd : 0)) * Y + (y0 + (row_ok ? hh : 0))) * X + x0;
-#pragma unroll
-            for (int i = 0; i < CONV_VX + 2; ++i) {
-                const int ww = w + i - 1;
-                in[i] = (row_ok && ww >= 0 && ww < W) ? __ldg(row + ww) : 0.0f;
-            }
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float k = c_conv_in_w[(zy * 3 + dx) * 32 + c];
-#pragma unroll
-                    for (int j = 0; j < CONV_VX; ++j) acc[j][c] = fmaf(in[j + dx], k, acc[j][c]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < CONV_VX; ++j) {
-            if (w + j >= W) break;
-            __half *o = raw + ((size_t)n * vox + ((size_t)d * H + h) * W + w + j) * 32;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = acc[j][q * 8 + e];
-                store8h(o + q * 8, f);
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                ssum[c] += acc[j][c];
-                ssq[c] = fmaf(acc[j][c], acc[j][c], ssq[c]);
-            }
-        }
-    }
-    block_reduce_atomic<32>(ssum, stats + (size_t)n * 32 * 2 + 0, 2);
-    block_reduce_atomic<32>(ssq, stats + (size_t)n * 32 * 2 + 1, 2);
-}
 
 // c8_0.conv1: 5 -> 5 on CUDA cores.  Input = relu(bn(raw8)) computed on the fly from the
 // fp32 [vox][8] output of c8_0.conv0 (stats8 has 16 columns per chunk), zero outside the
