@@ -406,9 +406,12 @@ static int launch_thin(const ThinArgs &a, cudaStream_t st) {
     return ISG_OK;
 }
 
+// grid = (blocks per chunk, N): ~48 blocks per SM over ALL chunks -- enough waves that kernels with
+// 2..8 resident blocks per SM balance, few enough that the per-block prologue (the chunk's
+// BatchNorm coefficient table) is not paid once per 256-thread sliver of every chunk
 static inline dim3 egrid(size_t work, int N) {
     size_t b = (work + 255) / 256;
-    const size_t cap = (size_t)num_sms() * 16;
+    const size_t cap = ((size_t)num_sms() * 48 + (size_t)N - 1) / (size_t)N;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return dim3((unsigned)b, (unsigned)N);
@@ -477,11 +480,11 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         const size_t work = vox(lc) * C / 8;
         const int off = u == 3 ? 1 : 0;
         if (u == 0)
-            bn_relu_up_kernel<2><<<egrid(work, N), 256, 0, st>>>(
+            bn_relu_up_kernel<2><<<egrid(work, N), 256, (size_t)(3 + 8) * C * sizeof(float), st>>>(
                 p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
         else
-            bn_relu_up_kernel<1><<<egrid(work, N), 256, 0, st>>>(
+            bn_relu_up_kernel<1><<<egrid(work, N), 256, (size_t)(3 + 4) * C * sizeof(float), st>>>(
                 p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
         ISG_LAUNCHED();

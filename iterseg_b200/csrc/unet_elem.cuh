@@ -46,33 +46,54 @@ __device__ __forceinline__ void store8h(__half *p, const float (&v)[8]) {
     *reinterpret_cast<uint4 *>(p) = u;
 }
 
-// shared scale/shift table for the chunk this block works on (C <= 256)
-__device__ __forceinline__ void bn_table(float *s_scale, float *s_shift, const unsigned long long *stats,
-                                         const float *gamma, const float *beta, int C, int n,
-                                         float inv_count) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
-        bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], inv_count, s_scale[c], s_shift[c]);
+// Shared scale/shift table for the chunk a block works on (C <= 256), as two float4 arrays per
+// quantity -- [scale | shift][half][C/8] -- so that the 8
+// channels of a thread are two float4 reads, consecutive lanes reading consecutive 16 bytes
+// (a scalar s_scale[c0 + j] read has lanes 32 bytes apart: an 8-way bank conflict).
+// Float index of channel c inside one quantity:
+__device__ __forceinline__ int bn_slot(int c, int groups) {
+    return ((c >> 2) & 1) * (groups * 4) + (c >> 3) * 4 + (c & 3);
+}
+__device__ __forceinline__ void bn_table4(float4 *tab, const unsigned long long *stats, const float *gamma,
+                                          const float *beta, int C, int n, float inv_count) {
+    float *t = reinterpret_cast<float *>(tab);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sc, sh;
+        bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], inv_count, sc, sh);
+        t[bn_slot(c, C / 8)] = sc;
+        t[C + bn_slot(c, C / 8)] = sh;
+    }
     __syncthreads();
+}
+// v = relu(v * scale + shift) for the 8 channels of group g
+__device__ __forceinline__ void bn_relu8(const float4 *tab, int groups, int g, float (&v)[8]) {
+    const float4 sc0 = tab[g], sc1 = tab[groups + g], sh0 = tab[2 * groups + g], sh1 = tab[3 * groups + g];
+    v[0] = fmaxf(fmaf(v[0], sc0.x, sh0.x), 0.0f);
+    v[1] = fmaxf(fmaf(v[1], sc0.y, sh0.y), 0.0f);
+    v[2] = fmaxf(fmaf(v[2], sc0.z, sh0.z), 0.0f);
+    v[3] = fmaxf(fmaf(v[3], sc0.w, sh0.w), 0.0f);
+    v[4] = fmaxf(fmaf(v[4], sc1.x, sh1.x), 0.0f);
+    v[5] = fmaxf(fmaf(v[5], sc1.y, sh1.y), 0.0f);
+    v[6] = fmaxf(fmaf(v[6], sc1.z, sh1.z), 0.0f);
+    v[7] = fmaxf(fmaf(v[7], sc1.w, sh1.w), 0.0f);
 }
 
 // raw -> relu(bn(raw)), same shape.  grid = (blocks, N)
 __global__ void __launch_bounds__(256)
 bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const unsigned long long *__restrict__ stats,
                const float *__restrict__ gamma, const float *__restrict__ beta, int C, size_t vox) {
-    __shared__ float s_scale[256], s_shift[256];
+    __shared__ float4 tab[128];                          // C <= 256
     const int n = blockIdx.y;
-    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    bn_table4(tab, stats, gamma, beta, C, n, 1.0f / (float)vox);
     const int groups = C / 8;
     const size_t total = vox * groups;
     const __half *src = raw + (size_t)n * vox * C;
     __half *dst = act + (size_t)n * vox * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % groups) * 8;
         float v[8];
         load8h(src + i * 8, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
+        bn_relu8(tab, groups, (int)(i % groups), v);
         store8h(dst + i * 8, v);
     }
 }
@@ -86,10 +107,10 @@ bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
                     __half *__restrict__ pooled, const unsigned long long *__restrict__ stats,
                     const float *__restrict__ gamma, const float *__restrict__ beta, int C, int D,
                     int H, int W, int Dc, int Hc, int Wc) {
-    __shared__ float s_scale[256], s_shift[256];
+    __shared__ float4 tab[128];                          // C <= 256
     const int n = blockIdx.y;
     const size_t vox = (size_t)D * H * W;
-    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    bn_table4(tab, stats, gamma, beta, C, n, 1.0f / (float)vox);
     const int groups = C / 8;
     const size_t total = (size_t)Dc * Hc * Wc * groups;
     const __half *src = raw + (size_t)n * vox * C;
@@ -105,12 +126,19 @@ bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = 0.0f;           // post-ReLU values are >= 0
+        const int g = c0 >> 3;
+        const float4 sc0 = tab[g], sc1 = tab[groups + g], sh0 = tab[2 * groups + g], sh1 = tab[3 * groups + g];
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
         for (int kz = 0; kz < PZ; ++kz) {
             const int d = dc * PZ + kz;
             if (d >= D) continue;
+#pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int h = 2 * hc - 1 + a;
                 if (h < 0 || h >= H) continue;
+#pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const int w = 2 * wc - 1 + b;
                     if (w < 0 || w >= W) continue;
@@ -119,7 +147,7 @@ bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
                     load8h(src + off, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        v[j] = fmaxf(fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
+                        v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.0f);
                         // the pooled tensor holds the max of the fp16-ROUNDED skip values so that
                         // it equals maxpool(skip) exactly
                         v[j] = __half2float(__float2half_rn(v[j]));
@@ -137,6 +165,11 @@ bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
 // groups = C)).  out[c, KZ*d+kz, 2h+a-off, 2w+b-off] = wgt[c,kz,a,b] * x[c,d,h,w] + bias[c];
 // off = 0 with crop [:-1,:-1] (up0..up2), off = 1 with crop [1:-1,1:-1] (up3).
 // One thread per (coarse voxel, 8 channels).  grid = (blocks, N)
+// All per-channel constants sit in shared memory as [table][half][C/8] float4 -- the 8 channels of
+// a thread are two float4 reads per table, consecutive lanes read consecutive 16 bytes (no bank
+// conflicts).  Reading the (C, KZ*4) weights straight from global memory costs 16 strided
+// 4-byte loads per tap, 32 sectors each: that, not HBM, bounded the first version (12x off the
+// roofline at C = 256).
 template <int KZ>
 __global__ void __launch_bounds__(256)
 bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
@@ -144,42 +177,65 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
                   const float *__restrict__ beta, const float *__restrict__ wgt,
                   const float *__restrict__ bias, int C, int Dc, int Hc, int Wc, int Df, int Hf,
                   int Wf, int off) {
-    __shared__ float s_scale[256], s_shift[256];
+    constexpr int TAPS = KZ * 4;
+    extern __shared__ float4 up_tab[];                  // [3 + TAPS][2][C/8]: scale, shift, bias, weights per tap
     const int n = blockIdx.y;
     const size_t vox = (size_t)Dc * Hc * Wc;
-    bn_table(s_scale, s_shift, stats, gamma, beta, C, n, 1.0f / (float)vox);
     const int groups = C / 8;
+    {
+        float *tab = reinterpret_cast<float *>(up_tab);
+        // channel c -> float index inside one table: [half = (c & 4) >> 2][group = c >> 3][c & 3]
+        auto slot = [&](int c) { return ((c >> 2) & 1) * (groups * 4) + (c >> 3) * 4 + (c & 3); };
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float sc, sh;
+            bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], 1.0f / (float)vox, sc, sh);
+            tab[0 * C + slot(c)] = sc;
+            tab[1 * C + slot(c)] = sh;
+            tab[2 * C + slot(c)] = bias[c];
+        }
+        for (int i = threadIdx.x; i < C * TAPS; i += blockDim.x) {
+            const int c = i / TAPS, tap = i - c * TAPS;
+            tab[(3 + tap) * C + slot(c)] = wgt[i];
+        }
+    }
+    __syncthreads();
     const size_t total = vox * groups;
     const __half *src = raw + (size_t)n * vox * C;
     __half *dst = up + (size_t)n * Df * Hf * Wf * C;
+    const int tstride = 2 * groups;                     // float4 per table
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % groups) * 8;
+        const int g = (int)(i % groups);
         size_t t = i / groups;
         const int wc = (int)(t % Wc); t /= Wc;
         const int hc = (int)(t % Hc);
         const int dc = (int)(t / Hc);
-        float x[8];
+        float x[8], bs[8];
         load8h(src + i * 8, x);
+        {
+            const float4 sc0 = up_tab[g], sc1 = up_tab[groups + g];
+            const float4 sh0 = up_tab[tstride + g], sh1 = up_tab[tstride + groups + g];
+            const float4 b0 = up_tab[2 * tstride + g], b1 = up_tab[2 * tstride + groups + g];
+            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = fmaxf(fmaf(x[j], s_scale[c0 + j], s_shift[c0 + j]), 0.0f);
-        for (int kz = 0; kz < KZ; ++kz) {
-            const int d = dc * KZ + kz;
-            if (d >= Df) continue;
-            for (int a = 0; a < 2; ++a) {
-                const int h = 2 * hc + a - off;
-                if (h < 0 || h >= Hf) continue;
-                for (int b = 0; b < 2; ++b) {
-                    const int w = 2 * wc + b - off;
-                    if (w < 0 || w >= Wf) continue;
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = fmaf(__ldg(wgt + (size_t)(c0 + j) * (KZ * 4) + kz * 4 + a * 2 + b), x[j],
-                                    __ldg(bias + c0 + j));
-                    store8h(dst + ((((size_t)d * Hf + h) * Wf + w) * C) + c0, o);
-                }
+            for (int j = 0; j < 8; ++j) {
+                x[j] = fmaxf(fmaf(x[j], sc[j], sh[j]), 0.0f);
+                bs[j] = bb[j];
             }
+        }
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) {
+            const int kz = tap >> 2, a = (tap >> 1) & 1, b = tap & 1;
+            const int d = dc * KZ + kz, h = 2 * hc + a - off, w = 2 * wc + b - off;
+            if (d >= Df || h < 0 || h >= Hf || w < 0 || w >= Wf) continue;
+            const float4 w0 = up_tab[(3 + tap) * tstride + g], w1 = up_tab[(3 + tap) * tstride + groups + g];
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(wv[j], x[j], bs[j]);
+            store8h(dst + ((((size_t)d * Hf + h) * Wf + w) * C) + g * 8, o);
         }
     }
 }

@@ -113,29 +113,41 @@ conv_in_tc_kernel(const ThinArgs a) {
         csum = csq = 0;
     };
 
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+    // unit index -> (chunk, plane, tile origin)
+    auto decode = [&](uint32_t u, int &n, int &d, int &h0, int &w0) {
         uint32_t t = u;
-        const int wb = (int)(t % (uint32_t)tiles_w); t /= (uint32_t)tiles_w;
-        const int hb = (int)(t % (uint32_t)tiles_h); t /= (uint32_t)tiles_h;
-        const int d = (int)(t % (uint32_t)D);
-        const int n = (int)(t / (uint32_t)D);
-        const int h0 = hb * 4, w0 = wb * 32;
+        w0 = (int)(t % (uint32_t)tiles_w) * 32; t /= (uint32_t)tiles_w;
+        h0 = (int)(t % (uint32_t)tiles_h) * 4; t /= (uint32_t)tiles_h;
+        d = (int)(t % (uint32_t)D);
+        n = (int)(t / (uint32_t)D);
+    };
+    // stage the input halo of unit u (zero outside the CHUNK: the reference pads the sliced chunk)
+    auto stage = [&](uint32_t u) {
+        int n, d, h0, w0;
+        decode(u, n, d, h0, w0);
+        const int z0 = __ldg(a.starts + n * 3 + 0), y0 = __ldg(a.starts + n * 3 + 1), x0 = __ldg(a.starts + n * 3 + 2);
+        float v[HSLOTS];
+#pragma unroll
+        for (int j = 0; j < HSLOTS; ++j) {
+            const int dd = d + (h_off[j] & 255) - 1, hh = h0 + ((h_off[j] >> 8) & 255) - 1, ww = w0 + (h_off[j] >> 16) - 1;
+            v[j] = 0.0f;
+            if (h_off[j] >= 0 && dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                v[j] = __ldg(a.src + ((size_t)(z0 + dd) * a.Y + (y0 + hh)) * a.X + (x0 + ww));
+        }
+#pragma unroll
+        for (int j = 0; j < HSLOTS; ++j)
+            if (h_off[j] >= 0) hin[tid + THIN_THREADS * j] = __half_as_ushort(__float2half_rn(v[j]));
+    };
+
+    if (blockIdx.x < units) stage(blockIdx.x);
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        int n, d, h0, w0;
+        decode(u, n, d, h0, w0);
         if (n != cur_n) {
             flush(cur_n);
             cur_n = n;
         }
-        // ---- stage the input halo (zero outside the CHUNK: the reference pads the sliced chunk) ----
-        const int z0 = a.starts[n * 3 + 0], y0 = a.starts[n * 3 + 1], x0 = a.starts[n * 3 + 2];
-#pragma unroll
-        for (int j = 0; j < HSLOTS; ++j) {
-            if (h_off[j] < 0) break;
-            const int dd = d + (h_off[j] & 255) - 1, hh = h0 + ((h_off[j] >> 8) & 255) - 1, ww = w0 + (h_off[j] >> 16) - 1;
-            float v = 0.0f;
-            if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
-                v = __ldg(a.src + ((size_t)(z0 + dd) * a.Y + (y0 + hh)) * a.X + (x0 + ww));
-            hin[tid + THIN_THREADS * j] = __half_as_ushort(__float2half_rn(v));
-        }
-        __syncthreads();
+        __syncthreads();                                 // the staged halo of this unit is complete
         // ---- im2col: row `tid` of A = the 27 taps around this thread's voxel ----
         uint32_t w32[16];
 #pragma unroll
@@ -159,6 +171,8 @@ conv_in_tc_kernel(const ThinArgs a) {
             umma_f16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
             umma_commit(bar);
         }
+        // the halo tile is free again: stage the next unit's while the MMAs run
+        if (u + gridDim.x < units) stage(u + gridDim.x);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
