@@ -16,6 +16,7 @@
 #include "unet_conv.cuh"
 #include "unet_elem.cuh"
 #include "unet_thin.cuh"
+#include "unet_zring.cuh"
 
 namespace isg {
 
@@ -110,6 +111,19 @@ static bool make_w_map(CUtensorMap *m, const void *base, int cin, int coutp, int
     return r == CUDA_SUCCESS;
 }
 
+// c8_0.conv0 weights packed [dy][80 rows][cin] (unet_zring.cuh): one box = (32 channels, 80 rows, 1 dy)
+static bool make_w_map_zring(CUtensorMap *m, const void *base, int cin) {
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)ZR_N, 3};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)ZR_N * cin * 2};
+    cuuint32_t box[3] = {32u, (cuuint32_t)ZR_N, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled(z-ring weights) -> %d", (int)r);
+    return r == CUDA_SUCCESS;
+}
+
 // ---- plan -------------------------------------------------------------------------------
 struct TcLayer {
     ConvGeom g;
@@ -118,6 +132,8 @@ struct TcLayer {
     int fold;
     size_t smem;
     int grid;
+    int zring;                   // 1: c8_0.conv0 runs conv3d_zring_kernel (unet_zring.cuh) with `zg`
+    ZringGeom zg;
 };
 
 }  // namespace isg
@@ -221,6 +237,31 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     TcLayer &t = p->tc[i];
     const int l = CONVS[i].level;
     const int cin = CONVS[i].cin;
+    t.zring = 0;
+    if (i == 16) {
+        // 64 -> 5 on [up3, skip0]: the z-ring kernel (nine (dz,dx) taps folded into N)
+        ZringGeom &z = t.zg;
+        z.N = p->N; z.D = p->D[l]; z.H = p->H[l]; z.W = p->W[l];
+        z.tiles_w = (z.W + ZR_WT - 1) / ZR_WT;
+        z.tiles_h = (z.H + ZR_HT - 1) / ZR_HT;
+        z.n_cols = z.N * z.tiles_h * z.tiles_w;
+        z.out = reinterpret_cast<float *>(out);
+        z.stats = p->stats[i];
+        z.sched = p->sched[i];
+        t.zring = 1;
+        t.cblk = 32;
+        t.fold = 0;
+        t.g = ConvGeom{};
+        t.smem = zring_smem_bytes();
+        t.grid = z.n_cols < num_sms() ? z.n_cols : num_sms();
+        if (c0 != 32 || c1 != 32 || out_mode != 1) {
+            set_error("conv %s: the z-ring kernel expects two 32-channel sources", CONVS[i].name);
+            return false;
+        }
+        return make_act_map(&t.tmA0, src0, 32, z.W, z.H, z.D, z.N, 32, ZR_P, ZR_HT) &&
+               make_act_map(&t.tmA1, src1, 32, z.W, z.H, z.D, z.N, 32, ZR_P, ZR_HT) &&
+               make_w_map_zring(&t.tmB, p->packed + p->L.w[i], cin);
+    }
     const int cblk = (c0 % 64 == 0 && (c1 % 64 == 0)) ? 64 : 32;
     t.cblk = cblk;
     ConvGeom &g = t.g;
@@ -353,6 +394,15 @@ static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
 }
 
 static int launch_tc(const TcLayer &t, cudaStream_t st) {
+    if (t.zring) {
+        ISG_CUDA(cudaFuncSetAttribute(conv3d_zring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+        int grid = t.grid;
+        const int avail = num_sms() - post_sms();
+        if (grid > avail) grid = avail;
+        conv3d_zring_kernel<<<grid, ZR_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.zg);
+        ISG_LAUNCHED();
+        return ISG_OK;
+    }
     const int G = t.g.taps_per_b;
     if (t.fold) {
         if (t.cblk == 64) return G == 9 ? launch_tc_inst<64, 9, true>(t, st) : launch_tc_inst<64, 3, true>(t, st);
@@ -536,7 +586,9 @@ extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, 
         const float *gam = (const float *)tensors[14 * mi + 4 + 5 * ci];
         const float *bet = (const float *)tensors[14 * mi + 5 + 5 * ci];
         ISG_REQUIRE(w && gam && bet, ISG_ERR_ARG, "isg_unet_weights_pack: missing tensor for %s", CONVS[i].name);
-        if (is_tc(i))
+        if (i == 16)
+            pack_conv_w_zring_kernel<<<64, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
+        else if (is_tc(i))
             pack_conv_w_kernel<<<256, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, cout_pad(i), CONVS[i].cin);
         else
             pack_conv_w_f32_kernel<<<16, 256, 0, st>>>(w, (float *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);

@@ -1,0 +1,315 @@
+// c8_0.conv0: conv3d 64 -> 5 (k=3, zero pad 1) on the concatenation [up3 (32 ch), c0 skip (32 ch)]
+// (src/iterseg/unet.py:93 of the last ConvModule; the cat is unet.py:345).
+//
+// With 5 output channels the generic kernel (unet_conv.cuh, dx-fold, N = 48) is bound by the
+// NUMBER of tcgen05.mma it issues -- 36 per 128 voxels at ~70 clocks each whatever their N --
+// and ran at 238 TFLOP/s, 1.75 ms per frame.  This kernel folds the NINE (dz,dx) taps into N:
+//   D_p[r, (dz,dx,co)] = sum_{dy,ci} A_p[r + dy*P, ci] * W[dz,dy,dx][ci,co]      (input plane p)
+//   out_z[r, co]       = sum_{dz,dx} D_{z+dz-1}[r + dx, (dz,dx,co)]
+// i.e. one accumulator per INPUT plane (N = 9 taps x 8 channels + 8 zero rows = 80 columns,
+// 12 MMAs per plane: 2 channel blocks x 3 dy x 2 K steps), kept in a RING of 6 accumulators while
+// the CTA walks a z-column of the chunk: output plane z is emitted once the accumulators of
+// planes z-1, z, z+1 are complete, reading the dz = 0 / 1 / 2 column blocks of the three, and an
+// accumulator is released after the third output plane that reads it.  The dx shift is the same
+// warp-shuffle row shift as in the dx-fold epilogue (a patch row is one warp, P = 32).
+// 36 -> 12 MMAs per 128 voxels.
+//
+// A: TMA halo planes {32 ch, P = 32, Ht + 2 = 6} (64-byte rows, hardware swizzle) through a ring
+//    of 6 slots, one per (plane, channel block).  B: the whole weight tensor resident in shared
+//    memory, packed [dy][(dz,dx) x 8 + co][cin] fp16 (pack_conv_w_zring_kernel).
+// Warp roles: 0 = A producer + column scheduler, 1 = MMA issuer, 2 = TMEM allocator,
+//             3 = B loader, 4..7 = epilogue.  Columns are handed out dynamically (see unet_conv.cuh).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace isg {
+
+struct ZringGeom {
+    int N, D, H, W;              // chunks, chunk extents
+    int tiles_w, tiles_h;
+    int n_cols;                  // N * tiles_h * tiles_w z-columns
+    float *out;                  // fp32 [N][vox][8]
+    unsigned long long *stats;   // [N][16][2] fixed point (see unet_conv.cuh)
+    unsigned int *sched;         // column counter, zeroed by the caller
+};
+
+static constexpr int ZR_P = 32, ZR_HT = 4, ZR_WT = 30;
+static constexpr int ZR_PLANE_ROWS = (ZR_HT + 2) * ZR_P;              // 192
+static constexpr int ZR_PLANE_BYTES = ZR_PLANE_ROWS * 64;             // 12288
+static constexpr int ZR_SLOTS = 6;
+static constexpr int ZR_NA = 6;                                       // accumulators in the ring
+static constexpr int ZR_N = 80;                                       // UMMA N
+static constexpr int ZR_B_STAGE = ZR_N * 64;                          // one (channel block, dy): 5120 B
+static constexpr int ZR_SCHED = 4;
+static constexpr int ZR_THREADS = 256;
+
+__host__ __device__ constexpr size_t zring_smem_bytes() {
+    return 1024 + (size_t)ZR_SLOTS * ZR_PLANE_BYTES + 6 * ZR_B_STAGE + 512 /* barriers */ +
+           4 * 32 * 9 * sizeof(float);
+}
+
+__global__ void __launch_bounds__(ZR_THREADS, 1)
+conv3d_zring_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const ZringGeom g) {
+    using namespace sm100;
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw_base = smem_u32(smem_dyn);
+    uint8_t *a_smem = smem_dyn + (((raw_base + 1023u) & ~1023u) - raw_base);
+    uint8_t *b_smem = a_smem + ZR_SLOTS * ZR_PLANE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_smem + 6 * ZR_B_STAGE);
+    uint64_t *plane_full = bars, *plane_empty = bars + ZR_SLOTS;
+    uint64_t *acc_full = bars + 2 * ZR_SLOTS, *acc_empty = acc_full + ZR_NA;
+    uint64_t *b_full = acc_empty + ZR_NA;
+    uint64_t *sched_full = b_full + 1, *sched_empty = sched_full + ZR_SCHED;
+    volatile int *sched_col = reinterpret_cast<volatile int *>(sched_empty + ZR_SCHED);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(sched_col) + ZR_SCHED);
+    float *stat_t = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = g.D;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0);
+        prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < ZR_SLOTS; ++i) {
+            mbar_init(&plane_full[i], 1);
+            mbar_init(&plane_empty[i], 1);
+        }
+        for (int i = 0; i < ZR_NA; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(b_full, 1);
+        for (int i = 0; i < ZR_SCHED; ++i) {
+            mbar_init(&sched_full[i], 1);
+            mbar_init(&sched_empty[i], 5);                 // MMA warp + 4 epilogue warps
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int col, int &wb, int &hb, int &n) {
+        wb = col % g.tiles_w;
+        const int t = col / g.tiles_w;
+        hb = t % g.tiles_h;
+        n = t / g.tiles_h;
+    };
+
+    if (warp == 0) {
+        // ===================== A producer + scheduler =====================
+        if (lane == 0) {
+            uint32_t lc = 0, sidx = 0;
+            int col = blockIdx.x;
+            for (;;) {
+                const uint32_t slot = sidx % ZR_SCHED;
+                mbar_wait(&sched_empty[slot], ((sidx / ZR_SCHED) & 1u) ^ 1u);
+                sched_col[slot] = col;
+                mbar_arrive(&sched_full[slot]);
+                ++sidx;
+                if (col >= g.n_cols) break;
+                const int next = (int)gridDim.x + (int)atomicAdd(g.sched, 1u);
+                int wb, hb, n;
+                decode(col, wb, hb, n);
+                for (int p = 0; p < D; ++p)
+                    for (int kb = 0; kb < 2; ++kb, ++lc) {
+                        const uint32_t s = lc % ZR_SLOTS;
+                        mbar_wait(&plane_empty[s], ((lc / ZR_SLOTS) & 1u) ^ 1u);
+                        mbar_expect_tx(&plane_full[s], ZR_PLANE_BYTES);
+                        tma_load_5d(a_smem + (size_t)s * ZR_PLANE_BYTES, kb == 0 ? &tmA0 : &tmA1, &plane_full[s],
+                                    0, wb * ZR_WT - 1, hb * ZR_HT - 1, p, n);
+                    }
+                col = next;
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== B loader (once) =====================
+        if (lane == 0) {
+            mbar_expect_tx(b_full, 6 * ZR_B_STAGE);
+            for (int kb = 0; kb < 2; ++kb)
+                for (int dy = 0; dy < 3; ++dy)
+                    tma_load_3d(b_smem + (size_t)(kb * 3 + dy) * ZR_B_STAGE, &tmB, b_full, kb * 32, 0, dy);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(128, ZR_N, 0 /* fp16 */);
+        const uint64_t dproto = make_kmajor_desc(0, 64, 0);
+        const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
+        const uint32_t a_lo = d_lo | (smem_u32(a_smem) >> 4);
+        const uint32_t b_lo = d_lo | (smem_u32(b_smem) >> 4);
+        constexpr uint32_t U = 64 >> 4;                        // one row in 16-byte units
+        uint32_t lc = 0, pc = 0;
+        mbar_wait(b_full, 0u);
+        for (uint32_t sidx = 0;; ++sidx) {
+            const uint32_t slot = sidx % ZR_SCHED;
+            mbar_wait(&sched_full[slot], (sidx / ZR_SCHED) & 1u);
+            const int col = sched_col[slot];
+            __syncwarp();
+            if (leader) mbar_arrive(&sched_empty[slot]);
+            if (col >= g.n_cols) break;
+            for (int p = 0; p < D; ++p, ++pc) {
+                const uint32_t a = pc % ZR_NA;
+                mbar_wait(&acc_empty[a], ((pc / ZR_NA) & 1u) ^ 1u);
+                const uint32_t tmem_d = tmem_base + a * ZR_N;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb, ++lc) {
+                    const uint32_t s = lc % ZR_SLOTS;
+                    mbar_wait(&plane_full[s], (lc / ZR_SLOTS) & 1u);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t a_pl = a_lo + s * (ZR_PLANE_BYTES >> 4);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t a_tap = a_pl + dy * ZR_P * U;
+                            const uint32_t b_tap = b_lo + (kb * 3 + dy) * (ZR_B_STAGE >> 4);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_f16(tmem_d, ((uint64_t)d_hi << 32) | (a_tap + 2 * k),
+                                         ((uint64_t)d_hi << 32) | (b_tap + 2 * k), idesc, (kb | dy | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&plane_empty[s]);
+                        if (kb == 1) umma_commit(&acc_full[a]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                         // TMEM lanes 32*ew .. 32*ew+31 = patch row ew
+        float *st = stat_t + ew * (32 * 9);
+        long long csum = 0, csq = 0;                     // lane < 8: channel `lane` of the current chunk
+        int cur_n = -1;
+        auto flush = [&](int n) {
+            if (n >= 0 && lane < 5) {
+                atomicAdd(g.stats + ((size_t)n * 16 + lane) * 2 + 0, (unsigned long long)csum);
+                atomicAdd(g.stats + ((size_t)n * 16 + lane) * 2 + 1, (unsigned long long)csq);
+            }
+            csum = csq = 0;
+        };
+        const size_t vox_chunk = (size_t)D * g.H * g.W;
+        uint32_t pc0 = 0;
+        for (uint32_t sidx = 0;; ++sidx) {
+            const uint32_t slot = sidx % ZR_SCHED;
+            mbar_wait(&sched_full[slot], (sidx / ZR_SCHED) & 1u);
+            const int col = sched_col[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sched_empty[slot]);
+            if (col >= g.n_cols) break;
+            int wb, hb, n;
+            decode(col, wb, hb, n);
+            if (n != cur_n) {
+                flush(cur_n);
+                cur_n = n;
+            }
+            const int h = hb * ZR_HT + ew, w = wb * ZR_WT + lane;
+            const bool valid = lane < ZR_WT && h < g.H && w < g.W;
+            int waited = 0;
+            for (int z = 0; z < D; ++z) {
+                const int need = z + 1 < D ? z + 1 : D - 1;
+                while (waited <= need) {
+                    const uint32_t q = pc0 + (uint32_t)waited;
+                    mbar_wait(&acc_full[q % ZR_NA], (q / ZR_NA) & 1u);
+                    ++waited;
+                }
+                tc_fence_after();
+                // S[dx][co] = sum over the input planes z-1, z, z+1 of their (dz, dx) column block:
+                // all loads are issued before the one wait
+                uint32_t v[3][3][8];
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const int p = z + dz - 1;
+                    if (p < 0 || p >= D) continue;                      // zero padding in z
+                    const uint32_t a = (pc0 + (uint32_t)p) % ZR_NA;
+                    const uint32_t taddr = tmem_base + a * ZR_N + dz * 24 + ((uint32_t)(ew * 32) << 16);
+                    tmem_ld_32x8(taddr, v[dz][0]);
+                    tmem_ld_32x8(taddr + 8, v[dz][1]);
+                    tmem_ld_32x8(taddr + 16, v[dz][2]);
+                }
+                tmem_ld_wait();
+                float S[3][8];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float acc = __uint_as_float(v[1][dx][j]);       // plane z always exists
+                        if (z >= 1) acc += __uint_as_float(v[0][dx][j]);
+                        if (z + 1 < D) acc += __uint_as_float(v[2][dx][j]);
+                        S[dx][j] = acc;
+                    }
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = S[0][j] + __shfl_down_sync(0xFFFFFFFFu, S[1][j], 1) + __shfl_down_sync(0xFFFFFFFFu, S[2][j], 2);
+                if (valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(g.out + ((size_t)n * vox_chunk + ((size_t)z * g.H + h) * g.W + w) * 8);
+                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) st[lane * 9 + j] = valid ? o[j] : 0.0f;
+                __syncwarp();
+                {   // lane = (quarter of the rows, channel): 8 rows each, then two shuffle steps
+                    const int c = lane & 7, r0 = (lane >> 3) * 8;
+                    float s = 0.0f, q2 = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float x = st[(r0 + r) * 9 + c];
+                        s += x;
+                        q2 = fmaf(x, x, q2);
+                    }
+                    s += __shfl_xor_sync(0xFFFFFFFFu, s, 8);
+                    q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, 8);
+                    s += __shfl_xor_sync(0xFFFFFFFFu, s, 16);
+                    q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, 16);
+                    csum += __float2ll_rn(s * 16777216.0f);            // lanes >= 8 hold copies; only lanes < 5 flush
+                    csq += __float2ll_rn(q2 * 16777216.0f);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (z >= 1) mbar_arrive(&acc_empty[(pc0 + (uint32_t)z - 1u) % ZR_NA]);
+                    if (z == D - 1) mbar_arrive(&acc_empty[(pc0 + (uint32_t)z) % ZR_NA]);
+                }
+            }
+            pc0 += (uint32_t)D;
+        }
+        flush(cur_n);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// nn.Conv3d weight (5, 64, 3,3,3) fp32 -> [dy][(dz*3 + dx) * 8 + co][cin] fp16, 80 rows per dy
+// (co >= 5 and rows >= 72 zero)
+__global__ void pack_conv_w_zring_kernel(const float *__restrict__ src, __half *__restrict__ dst, int cout, int cin) {
+    const int total = 3 * ZR_N * cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % cin;
+        const int row = (i / cin) % ZR_N;
+        const int dy = i / (cin * ZR_N);
+        const int co = row & 7, t9 = row >> 3;              // t9 = dz * 3 + dx
+        float v = 0.0f;
+        if (t9 < 9 && co < cout) {
+            const int dz = t9 / 3, dx = t9 % 3;
+            v = src[((size_t)co * cin + ci) * 27 + dz * 9 + dy * 3 + dx];
+        }
+        dst[i] = __float2half_rn(v);
+    }
+}
+
+}  // namespace isg
