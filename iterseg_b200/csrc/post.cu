@@ -50,37 +50,44 @@ __global__ void ord_to_float_kernel(const uint32_t *__restrict__ in, float *__re
     if (i < n) out[i] = ord_f32(in[i]);
 }
 
-// 3x3x3 peaks of the smoothed centre map (peak_local_max)
+// 3x3x3 peaks of the smoothed centre map (peak_local_max):
+// candidates = interior voxels > thr that no voxel of their 3x3x3 neighbourhood exceeds.
+// `nontrivial` reproduces skimage's "every voxel equals its local maximum -> no peaks" rule: on a
+// connected grid that happens exactly when the image is constant, i.e. no voxel differs from
+// voxel 0.  Only voxels above the threshold (few) pay for the 26 neighbour loads.
+// One warp per (z, y) row, lanes along x.
 __global__ void __launch_bounds__(256)
 local_max_kernel(const float *__restrict__ cs, uint32_t Z, uint32_t Y, uint32_t X, float thr,
                  uint64_t *__restrict__ cand, uint32_t cap, uint32_t *__restrict__ n_cand,
                  uint32_t *__restrict__ nontrivial) {
-    const uint64_t n = (uint64_t)Z * Y * X;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    bool saw_nonmax = false;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
-        uint32_t x = (uint32_t)(v % X);
-        uint64_t t = v / X;
-        uint32_t y = (uint32_t)(t % Y);
-        uint32_t z = (uint32_t)(t / Y);
-        const float c = cs[v];
-        bool is_max = true;
-        const uint32_t z0 = z ? z - 1 : 0, z1 = z + 1 < Z ? z + 1 : Z - 1;
-        const uint32_t y0 = y ? y - 1 : 0, y1 = y + 1 < Y ? y + 1 : Y - 1;
-        const uint32_t x0 = x ? x - 1 : 0, x1 = x + 1 < X ? x + 1 : X - 1;
-        for (uint32_t zz = z0; zz <= z1; ++zz)
-            for (uint32_t yy = y0; yy <= y1; ++yy) {
-                const float *row = cs + ((uint64_t)zz * Y + yy) * X;
-                for (uint32_t xx = x0; xx <= x1; ++xx) is_max &= !(__ldg(row + xx) > c);
+    const uint32_t rows = Z * Y;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const float c0 = __ldg(cs);
+    bool differs = false;
+    for (uint32_t row = wid; row < rows; row += nw) {
+        const uint32_t z = row / Y, y = row - z * Y;
+        const float *r = cs + (uint64_t)row * X;
+        const bool row_interior = z > 0 && z + 1 < Z && y > 0 && y + 1 < Y;
+        for (uint32_t x = lane; x < X; x += 32) {
+            const float c = r[x];
+            differs |= c != c0;
+            if (!(row_interior && x > 0 && x + 1 < X && c > thr)) continue;
+            bool is_max = true;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const float *q = r + ((int64_t)dz * Y + dy) * (int64_t)X + x;
+                    is_max &= !(__ldg(q - 1) > c) & !(__ldg(q) > c) & !(__ldg(q + 1) > c);
+                }
+            if (is_max) {
+                uint32_t slot = atomicAdd(n_cand, 1u);
+                if (slot < cap) cand[slot] = ((uint64_t)(~f32_ord(c)) << 32) | ((uint64_t)row * X + x);
             }
-        if (!is_max) saw_nonmax = true;
-        const bool interior = z > 0 && z + 1 < Z && y > 0 && y + 1 < Y && x > 0 && x + 1 < X;
-        if (is_max && interior && c > thr) {
-            uint32_t slot = atomicAdd(n_cand, 1u);
-            if (slot < cap) cand[slot] = ((uint64_t)(~f32_ord(c)) << 32) | (uint64_t)v;
         }
     }
-    if (__any_sync(0xFFFFFFFFu, saw_nonmax) && (threadIdx.x & 31) == 0) atomicOr(nontrivial, 1u);
+    if (__any_sync(0xFFFFFFFFu, differs) && lane == 0) atomicOr(nontrivial, 1u);
 }
 
 // numpy.histogram(smoothed, 256) bin index (uniform-bin fast path, float32)
