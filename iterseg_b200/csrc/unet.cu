@@ -553,11 +553,23 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         }
     }
     // ---- c8_0.conv1 (5 -> 5) + BN + sigmoid + placement ----
-    ISG_CUDA(cudaMemcpyToSymbolAsync(c_conv_out_w, pk + L.w[17], sizeof(float) * 27 * 25, 0, cudaMemcpyDeviceToDevice, st));
-    conv_out_kernel<<<egrid(vox(0) / CONV_VX, N), 256, 0, st>>>(p->raw8, p->stats[16], G(16), B(16),
-                                                      reinterpret_cast<const float *>(pk + L.w[17]),
-                                                      p->raw9, p->stats[17], p->D[0], p->H[0], p->W[0]);
-    ISG_LAUNCHED();
+    {
+        ZoutArgs a{};
+        ZringGeom &z = a.g;
+        z.N = N; z.D = p->D[0]; z.H = p->H[0]; z.W = p->W[0];
+        z.tiles_w = (z.W + ZR_WT - 1) / ZR_WT;
+        z.tiles_h = (z.H + ZR_HT - 1) / ZR_HT;
+        z.n_cols = z.N * z.tiles_h * z.tiles_w;
+        z.out = p->raw9; z.stats = p->stats[17]; z.sched = p->sched[17];
+        a.src = p->raw8; a.stats_in = p->stats[16]; a.gamma_in = G(16); a.beta_in = B(16);
+        a.wgt = reinterpret_cast<const float *>(pk + L.w[17]);
+        ISG_CUDA(cudaFuncSetAttribute(conv_out_zring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)zout_smem_bytes()));
+        int grid = 2 * (num_sms() - post_sms());
+        if (grid > z.n_cols) grid = z.n_cols;
+        conv_out_zring_kernel<<<grid, ZO_THREADS, zout_smem_bytes(), st>>>(a);
+        ISG_LAUNCHED();
+    }
     if (feats == nullptr) return ISG_OK;
     place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), p->starts,
                                                    p->crop_lo, p->crop_hi, feats, p->Z, p->Y, p->X,

@@ -1,8 +1,8 @@
 // Memory-bound companions of the tensor-core convolutions (all channels-last fp16,
 // fp32 math): train-mode BatchNorm apply + ReLU, fused with max-pool (encoder) or
-// with the depthwise transposed convolution + crop (decoder); the 5 -> 5 CUDA-core
-// convolution (c0.conv0, 1 -> 32, is an im2col tensor-core kernel: unet_thin.cuh); the final
-// BatchNorm + sigmoid + crop-and-place.
+// with the depthwise transposed convolution + crop (decoder); the final BatchNorm + sigmoid +
+// crop-and-place.  (The two thin convolutions are tensor-core kernels of their own: c0.conv0 in
+// unet_thin.cuh, c8_0.conv1 in unet_zring.cuh.)
 //
 // Reference: ConvModule.forward (src/iterseg/unet.py:91-106), MaxPool3d layers
 // (unet.py:166-187), ConvTranspose3d layers (unet.py:216-242), crops + concat
@@ -238,118 +238,6 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
             store8h(dst + ((((size_t)d * Hf + h) * Wf + w) * C) + g * 8, o);
         }
     }
-}
-
-// block-wide reduction of NV per-thread partial sums -> atomicAdd into dst[i*stride]
-template <int NV>
-__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], unsigned long long *dst, int stride) {
-    __shared__ float red[8][NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float x = v[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-        if (lane == 0) red[warp][i] = x;
-    }
-    __syncthreads();
-    const int nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
-        float x = 0.0f;
-        for (int w = 0; w < nw; ++w) x += red[w][i];
-        atomicAdd(dst + (size_t)i * stride, (unsigned long long)__float2ll_rn(x * 16777216.0f));
-    }
-    __syncthreads();
-}
-
-// c8_0.conv1 keeps its weights in constant memory: after unrolling every weight is an immediate
-// constant-bank operand of its FFMA (all lanes use the same weight at the same time), so no load
-// instruction and no register is spent on it.  Uploaded per forward (unet.cu).
-__constant__ float c_conv_out_w[27 * 25];
-
-// Each thread computes CONV_VX voxels, so that a weight feeds CONV_VX FMAs per channel.
-static constexpr int CONV_VX = 4;
-
-// c8_0.conv1: 5 -> 5 on CUDA cores.  Input = relu(bn(raw8)) computed on the fly from the
-// fp32 [vox][8] output of c8_0.conv0 (stats8 has 16 columns per chunk), zero outside the
-// chunk.  Output raw9 fp32 [vox][8] + statistics [N][5][2].   grid = (blocks, N)
-__global__ void __launch_bounds__(256)
-conv_out_kernel(const float *__restrict__ raw8, const unsigned long long *__restrict__ stats8,
-                const float *__restrict__ gamma8, const float *__restrict__ beta8,
-                const float *__restrict__ wgt /* [27][5 in][5 out] */, float *__restrict__ raw9,
-                unsigned long long *__restrict__ stats9, int D, int H, int W) {
-    __shared__ float sc[5], sh[5];
-    const int n = blockIdx.y;
-    const size_t vox = (size_t)D * H * W;
-    if (threadIdx.x < 5)
-        bn_coeffs(stats8 + ((size_t)n * 16 + threadIdx.x) * 2, gamma8[threadIdx.x], beta8[threadIdx.x],
-                  1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
-    __syncthreads();
-    float ssum[5], ssq[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) ssum[c] = ssq[c] = 0.0f;
-    const float *src = raw8 + (size_t)n * vox * 8;
-    // a thread computes CONV_VX voxels stacked along y (x stays the fastest index across threads,
-    // so every load and store is coalesced): an input position feeds up to 3 of them, a weight
-    // read from shared memory feeds all of them
-    const int hq = (H + CONV_VX - 1) / CONV_VX;
-    const size_t units = (size_t)D * hq * W;
-    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units;
-         u += (size_t)gridDim.x * blockDim.x) {
-        const int w = (int)(u % W);
-        const size_t t = u / W;
-        const int h = (int)(t % hq) * CONV_VX;
-        const int d = (int)(t / hq);
-        float acc[CONV_VX][5];
-#pragma unroll
-        for (int j = 0; j < CONV_VX; ++j)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) acc[j][c] = 0.f;
-#pragma unroll
-        for (int dz = 0; dz < 3; ++dz) {
-            const int dd = d + dz - 1;
-            if (dd < 0 || dd >= D) continue;
-#pragma unroll
-            for (int r = 0; r < CONV_VX + 2; ++r) {
-                const int hh = h + r - 1;
-                if (hh < 0 || hh >= H) continue;
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int ww = w + dx - 1;
-                    if (ww < 0 || ww >= W) continue;
-                    const float4 *p = reinterpret_cast<const float4 *>(src + (((size_t)dd * H + hh) * W + ww) * 8);
-                    const float4 lo = __ldg(p), hi = __ldg(p + 1);
-                    const float a[5] = {fmaxf(fmaf(lo.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(lo.y, sc[1], sh[1]), 0.f),
-                                        fmaxf(fmaf(lo.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(lo.w, sc[3], sh[3]), 0.f),
-                                        fmaxf(fmaf(hi.x, sc[4], sh[4]), 0.f)};
-#pragma unroll
-                    for (int j = 0; j < CONV_VX; ++j) {
-                        const int dy = r - j;                   // this row is tap dy of output row h + j
-                        if (dy < 0 || dy > 2) continue;
-                        const float *k = c_conv_out_w + ((dz * 3 + dy) * 3 + dx) * 25;
-#pragma unroll
-                        for (int ci = 0; ci < 5; ++ci)
-#pragma unroll
-                            for (int co = 0; co < 5; ++co) acc[j][co] = fmaf(a[ci], k[ci * 5 + co], acc[j][co]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < CONV_VX; ++j) {
-            if (h + j >= H) break;
-            float4 *o = reinterpret_cast<float4 *>(raw9 + ((size_t)n * vox + ((size_t)d * H + h + j) * W + w) * 8);
-            o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            o[1] = make_float4(acc[j][4], 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                ssum[c] += acc[j][c];
-                ssq[c] = fmaf(acc[j][c], acc[j][c], ssq[c]);
-            }
-        }
-    }
-    block_reduce_atomic<5>(ssum, stats9 + (size_t)n * 5 * 2 + 0, 2);
-    block_reduce_atomic<5>(ssq, stats9 + (size_t)n * 5 * 2 + 1, 2);
 }
 
 // sigmoid(bn(raw9)) -> the cropped interior of every chunk is placed into the
