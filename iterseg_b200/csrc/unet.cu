@@ -253,7 +253,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
         t.fold = 0;
         t.g = ConvGeom{};
         t.smem = zring_smem_bytes();
-        t.grid = z.n_cols < num_sms() ? z.n_cols : num_sms();
+        t.grid = z.n_cols < 2 * num_sms() ? z.n_cols : 2 * num_sms();      // two CTAs per SM
         if (c0 != 32 || c1 != 32 || out_mode != 1) {
             set_error("conv %s: the z-ring kernel expects two 32-channel sources", CONVS[i].name);
             return false;
@@ -397,7 +397,7 @@ static int launch_tc(const TcLayer &t, cudaStream_t st) {
     if (t.zring) {
         ISG_CUDA(cudaFuncSetAttribute(conv3d_zring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
         int grid = t.grid;
-        const int avail = num_sms() - post_sms();
+        const int avail = 2 * (num_sms() - post_sms());
         if (grid > avail) grid = avail;
         conv3d_zring_kernel<<<grid, ZR_THREADS, t.smem, st>>>(t.tmA0, t.tmA1, t.tmB, t.zg);
         ISG_LAUNCHED();

@@ -7,15 +7,16 @@
 //   D_p[r, (dz,dx,co)] = sum_{dy,ci} A_p[r + dy*P, ci] * W[dz,dy,dx][ci,co]      (input plane p)
 //   out_z[r, co]       = sum_{dz,dx} D_{z+dz-1}[r + dx, (dz,dx,co)]
 // i.e. one accumulator per INPUT plane (N = 9 taps x 8 channels + 8 zero rows = 80 columns,
-// 12 MMAs per plane: 2 channel blocks x 3 dy x 2 K steps), kept in a RING of 6 accumulators while
+// 12 MMAs per plane: 2 channel blocks x 3 dy x 2 K steps), kept in a RING of 3 accumulators (256 TMEM
+// columns, so TWO CTAs share an SM and fill each other's MMA -> epilogue bubbles) while
 // the CTA walks a z-column of the chunk: output plane z is emitted once the accumulators of
 // planes z-1, z, z+1 are complete, reading the dz = 0 / 1 / 2 column blocks of the three, and an
 // accumulator is released after the third output plane that reads it.  The dx shift is the same
 // warp-shuffle row shift as in the dx-fold epilogue (a patch row is one warp, P = 32).
-// 36 -> 12 MMAs per 128 voxels.
+// 36 -> 12 MMAs per 128 voxels: 1.75 -> 1.07 ms (one CTA per SM, ring of 6) -> 0.95 ms (two per SM).
 //
 // A: TMA halo planes {32 ch, P = 32, Ht + 2 = 6} (64-byte rows, hardware swizzle) through a ring
-//    of 6 slots, one per (plane, channel block).  B: the whole weight tensor resident in shared
+//    of 4 slots, one per (plane, channel block).  B: the whole weight tensor resident in shared
 //    memory, packed [dy][(dz,dx) x 8 + co][cin] fp16 (pack_conv_w_zring_kernel).
 // Warp roles: 0 = A producer + column scheduler, 1 = MMA issuer, 2 = TMEM allocator,
 //             3 = B loader, 4..7 = epilogue.  Columns are handed out dynamically (see unet_conv.cuh).
@@ -40,8 +41,11 @@ struct ZringGeom {
 static constexpr int ZR_P = 32, ZR_HT = 4, ZR_WT = 30;
 static constexpr int ZR_PLANE_ROWS = (ZR_HT + 2) * ZR_P;              // 192
 static constexpr int ZR_PLANE_BYTES = ZR_PLANE_ROWS * 64;             // 12288
-static constexpr int ZR_SLOTS = 6;
-static constexpr int ZR_NA = 6;                                       // accumulators in the ring
+static constexpr int ZR_SLOTS = 4;                                    // plane slots per CTA
+static constexpr int ZR_NA = 3;                                       // accumulators in the ring: 3 x 80 columns ->
+                                                                      // 256 TMEM columns, TWO CTAs per SM (they fill
+                                                                      // each other's MMA -> epilogue bubbles)
+static constexpr int ZR_TMEM_COLS = 256;
 static constexpr int ZR_N = 80;                                       // UMMA N
 static constexpr int ZR_B_STAGE = ZR_N * 64;                          // one (channel block, dy): 5120 B
 static constexpr int ZR_SCHED = 4;
@@ -187,7 +191,7 @@ __device__ __forceinline__ void zring_epilogue(const ZringGeom &g, uint32_t tmem
     flush(cur_n);
 }
 
-__global__ void __launch_bounds__(ZR_THREADS, 1)
+__global__ void __launch_bounds__(ZR_THREADS, 2)
 conv3d_zring_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ZringGeom g) {
     using namespace sm100;
@@ -229,7 +233,7 @@ conv3d_zring_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, ZR_TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -325,12 +329,12 @@ conv3d_zring_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        zring_epilogue<ZR_NA, 16, true>(g, tmem_base, acc_full, acc_empty, sched_full, sched_empty, sched_col,
+        zring_epilogue<ZR_NA, 16, false>(g, tmem_base, acc_full, acc_empty, sched_full, sched_empty, sched_col,
                                   stat_t + (warp - 4) * (32 * 9), warp - 4, lane);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, ZR_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
