@@ -17,6 +17,7 @@
 #include "unet_elem.cuh"
 #include "unet_thin.cuh"
 #include "unet_zring.cuh"
+#include "unet_zring32.cuh"
 
 namespace isg {
 
@@ -124,6 +125,19 @@ static bool make_w_map_zring(CUtensorMap *m, const void *base, int cin) {
     return r == CUDA_SUCCESS;
 }
 
+// 32 -> 32 z-ring weights packed [dy*3+dx][96 rows][32] (unet_zring32.cuh): one box = one tap
+static bool make_w_map_z32(CUtensorMap *m, const void *base) {
+    cuuint64_t dims[3] = {32, (cuuint64_t)Z32_N, 9};
+    cuuint64_t strides[2] = {32 * 2, (cuuint64_t)Z32_N * 32 * 2};
+    cuuint32_t box[3] = {32u, (cuuint32_t)Z32_N, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled(z-ring 32->32 weights) -> %d", (int)r);
+    return r == CUDA_SUCCESS;
+}
+
 // ---- plan -------------------------------------------------------------------------------
 struct TcLayer {
     ConvGeom g;
@@ -134,6 +148,7 @@ struct TcLayer {
     int grid;
     int zring;                   // 1: c8_0.conv0 runs conv3d_zring_kernel (unet_zring.cuh) with `zg`
     ZringGeom zg;
+    Z32Args z32;                 // zring == 2: c0.conv1 / c7_0.conv1 run conv3d_zring32_kernel (unet_zring32.cuh)
 };
 
 }  // namespace isg
@@ -238,6 +253,29 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     const int l = CONVS[i].level;
     const int cin = CONVS[i].cin;
     t.zring = 0;
+    if ((i == 1 || i == 15) && getenv("ISG_NO_ZRING32") == nullptr) {
+        // 32 -> 32 at the two finest levels: dz folded into N on a TMEM ring (unet_zring32.cuh)
+        Z32Args &z = t.z32;
+        z.N = p->N; z.D = p->D[l]; z.H = p->H[l]; z.W = p->W[l];
+        z.tiles_w = (z.W + ZR_WT - 1) / ZR_WT;
+        z.tiles_h = (z.H + ZR_HT - 1) / ZR_HT;
+        z.n_cols = z.N * z.tiles_h * z.tiles_w;
+        z.out = reinterpret_cast<__half *>(out);
+        z.stats = p->stats[i];
+        z.sched = p->sched[i];
+        t.zring = 2;
+        t.cblk = 32;
+        t.fold = 0;
+        t.g = ConvGeom{};
+        t.smem = z32_smem_bytes();
+        t.grid = z.n_cols < num_sms() ? z.n_cols : num_sms();
+        if (c0 != 32 || c1 != 0 || out_mode != 0 || CONVS[i].cout != 32) {
+            set_error("conv %s: the 32 -> 32 z-ring kernel does not fit", CONVS[i].name);
+            return false;
+        }
+        return make_act_map(&t.tmA0, src0, 32, z.W, z.H, z.D, z.N, 32, ZR_P, ZR_HT) &&
+               make_w_map_z32(&t.tmB, p->packed + p->L.w[i]);
+    }
     if (i == 16) {
         // 64 -> 5 on [up3, skip0]: the z-ring kernel (nine (dz,dx) taps folded into N)
         ZringGeom &z = t.zg;
@@ -394,6 +432,15 @@ static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
 }
 
 static int launch_tc(const TcLayer &t, cudaStream_t st) {
+    if (t.zring == 2) {
+        ISG_CUDA(cudaFuncSetAttribute(conv3d_zring32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+        int grid = t.grid;
+        const int avail = num_sms() - post_sms();
+        if (grid > avail) grid = avail;
+        conv3d_zring32_kernel<<<grid, Z32_THREADS, t.smem, st>>>(t.tmA0, t.tmB, t.z32);
+        ISG_LAUNCHED();
+        return ISG_OK;
+    }
     if (t.zring) {
         ISG_CUDA(cudaFuncSetAttribute(conv3d_zring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
         int grid = t.grid;
@@ -598,7 +645,9 @@ extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, 
         const float *gam = (const float *)tensors[14 * mi + 4 + 5 * ci];
         const float *bet = (const float *)tensors[14 * mi + 5 + 5 * ci];
         ISG_REQUIRE(w && gam && bet, ISG_ERR_ARG, "isg_unet_weights_pack: missing tensor for %s", CONVS[i].name);
-        if (i == 16)
+        if ((i == 1 || i == 15) && getenv("ISG_NO_ZRING32") == nullptr)
+            pack_conv_w_zring32_kernel<<<64, 256, 0, st>>>(w, (__half *)(pk + L.w[i]));
+        else if (i == 16)
             pack_conv_w_zring_kernel<<<64, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
         else if (is_tc(i))
             pack_conv_w_kernel<<<256, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, cout_pad(i), CONVS[i].cin);
