@@ -574,7 +574,6 @@ extern "C" int isg_slab_stats(const float *feats, int n_chan, int64_t z, int64_t
     ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE, "isg_slab_stats: workspace too small (%zu < %zu)",
                 workspace_bytes, cv.off);
     const int sms = num_sms();
-    const int grid = sms * 8;
     GaussW g2;
     g2.r = prm->r2;
     for (int i = 0; i <= prm->r2; ++i) g2.w[i] = gauss2_host[i];
