@@ -350,7 +350,7 @@ def run_gpu(args, rank, local_rank, world):
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': ach_tf / peak_tf if peak_tf else None, 'traffic': conv_traffic(),
-                         'kernel': 'conv3d_tc_kernel x15 + conv3d_zring_kernel (the 16 tcgen05 implicit-GEMM launches per step)',
+                         'kernel': 'conv3d_tc_kernel x13 + conv3d_zring32_kernel x2 + conv3d_zring_kernel (the 16 TMA-fed tcgen05 implicit-GEMM launches per step)',
                          'peak_source': f'{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)',
                          'share_of_step': (tc_ms / n_fw) / ms_step if n_fw else None,
                          'unet_ms_per_step': fw_ms / n_fw if n_fw else None},

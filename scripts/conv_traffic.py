@@ -26,7 +26,7 @@ def val(r, name, scale_to=None):
 layers = []
 for r in data:
     name = r[col['Kernel Name']]
-    if 'conv3d_tc' not in name and 'conv3d_zring' not in name:
+    if 'conv3d_tc' not in name and 'conv3d_zring' not in name:      # conv3d_zring32 matches too
         continue
     layers.append({
         'kernel': name[:64],
@@ -39,7 +39,7 @@ for r in data:
 layers = layers[:16]
 out = {
     'source': f'{sys.argv[1]} (ncu --set full, scripts/time_unet.py, one frame = 36 chunks)',
-    'kernel': 'conv3d_tc_kernel x15 + conv3d_zring_kernel',
+    'kernel': 'conv3d_tc_kernel + conv3d_zring32_kernel + conv3d_zring_kernel',
     'launches': len(layers),
     'dram_bytes_per_launch': sum((l['dram_r_gb'] + l['dram_w_gb']) * 1e9 for l in layers) / max(len(layers), 1),
     'layers': layers,
