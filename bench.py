@@ -49,17 +49,6 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
-def conv_traffic():
-    """DRAM bytes per conv3d_tc launch (average over the 16 layers) from the committed
-    `ncu --set full` capture of the same kernels (profiles/r01_conv_traffic.json), else None."""
-    fn = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
-    try:
-        with open(fn) as f:
-            return float(json.load(f)['dram_bytes_per_launch'])
-    except Exception:
-        return None
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -129,56 +118,76 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # CPU reference arm (the oracle port of the reference, oracle/*)
 # --------------------------------------------------------------------------------------
-def cpu_reference_step(vol, labels_gt, sd, n_sample_chunks, threads):
-    """One bounded sample of the reference CPU path on this frame: `n_sample_chunks` of the
-    36 U-Net chunks (fp32 torch/oneDNN, train-mode BN, as predict.py:100-126 with the U-Net
-    on the CPU) + the whole post-U-Net stage (watershed.py:165-223) on analytic feature maps
-    of the same frame.  Returns the extrapolated seconds per frame and the split."""
+def cpu_unet_chunks(vol, sd, starts, threads):
+    """fp32 torch/oneDNN U-Net with train-mode BN on the given chunks (predict.py:100-126 with the
+    network on the CPU).  Returns (seconds per chunk, list of (5,cz,cy,cx) predictions)."""
     import torch
-    from oracle import chunks as ochunks, post as opost, unet_ref
-    from iterseg_b200 import synth
+    from oracle import unet_ref
     torch.set_num_threads(threads)
-    starts, _ = ochunks.make_chunks(vol.shape, CHUNK, MARGIN)
-    pick = [starts[i] for i in np.linspace(0, len(starts) - 1, n_sample_chunks).astype(int)]
+    preds = []
     t0 = time.perf_counter()
-    for st in pick:
+    for st in starts:
         sl = tuple(slice(s, s + c) for s, c in zip(st, CHUNK))
         x = torch.from_numpy(np.ascontiguousarray(vol[sl])[None, None])
-        unet_ref.unet_forward(x, sd)
-    t_unet = (time.perf_counter() - t0) / len(pick)
-    feats = synth.analytic_features(labels_gt, 0)
-    out = np.zeros(tuple(s + 2 for s in vol.shape), np.uint32)
+        preds.append(unet_ref.unet_forward(x, sd)[0].numpy())
+    return (time.perf_counter() - t0) / max(len(starts), 1), preds
+
+
+def cpu_post(feats):
+    """The whole post-U-Net stage (watershed.py:165-223: scipy/numpy restatement + C heap flood,
+    one thread like the numba original) on a (5,Z,Y,X) feature volume.  Returns seconds."""
+    from oracle import post as opost
+    out = np.zeros(tuple(s + 2 for s in feats.shape[1:]), np.uint32)
     t0 = time.perf_counter()
     opost.segment_output_image(feats, out=out.ravel())
-    t_post = time.perf_counter() - t0
-    per_frame = t_unet * len(starts) + t_post
-    return per_frame, t_unet, t_post, len(starts)
+    return time.perf_counter() - t0, out
 
 
 def run_reference(args, rank):
+    """The reference's CPU path on this box's host cores.  One FULL frame is computed once (all 36
+    chunks: an un-extrapolated measurement, and the network-derived feature volume the post stage
+    runs on -- the same kind of features the GPU arm's post stage sees); every timed step then
+    repeats a bounded sample (2 chunks + the whole post stage) and is extrapolated to a frame."""
     if rank != 0:
         return 0
     from iterseg_b200 import synth
-    from oracle import flood as oflood
+    from oracle import chunks as ochunks, flood as oflood
     oflood.build()
     threads = os.cpu_count() or 1
-    vol, lab = synth.platelet_frame(FRAME, seed=0, return_labels=True)
+    vol = synth.platelet_frame(FRAME, seed=0)
     sd = synth.structured_state_dict(0)
+    starts, crops = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
+    n_chunks = len(starts)
+    # ---- one whole frame, timed as it is ----
+    t0 = time.perf_counter()
+    t_chunk_full, preds = cpu_unet_chunks(vol, sd, starts, threads)
+    feats = np.zeros((5,) + FRAME, np.float32)
+    for st, cr, pr in zip(starts, crops, preds):
+        sl = tuple(slice(s, s + c) for s, c in zip(st, CHUNK))
+        crs = (slice(None),) + tuple(slice(a, b) for a, b in cr)
+        feats[(slice(None),) + sl][crs] = pr[crs]
+    del preds
+    t_post_full, _ = cpu_post(feats)
+    full_frame_s = time.perf_counter() - t0
     n_sample = 2
-    for _ in range(args.warmup):
-        cpu_reference_step(vol, lab, sd, 1, threads)
+    pick = [starts[i] for i in np.linspace(0, n_chunks - 1, n_sample).astype(int)]
+    for _ in range(max(args.warmup - 1, 0)):                       # the full frame above was warm-up no. 1
+        cpu_unet_chunks(vol, sd, pick[:1], threads)
     times, splits = [], []
     for _ in range(args.steps):
-        per_frame, t_unet, t_post, n_chunks = cpu_reference_step(vol, lab, sd, n_sample, threads)
-        times.append(per_frame)
+        t_unet, _ = cpu_unet_chunks(vol, sd, pick, threads)
+        t_post, _ = cpu_post(feats)
+        times.append(t_unet * n_chunks + t_post)
         splits.append((t_unet, t_post))
     per_frame = float(np.mean(times))
     nvox = float(np.prod(FRAME))
     value = nvox / per_frame
-    sample = (f'{n_sample} of {n_chunks} U-Net chunks per step timed (fp32 torch CPU, train-mode BN) and '
-              f'extrapolated x{n_chunks}/{n_sample}; full post-U-Net stage (scipy/numpy + C heap flood, '
-              f'single thread like the numba original) on analytic feature maps of the same frame; '
-              f'mean U-Net {np.mean([s[0] for s in splits]):.2f} s/chunk, post {np.mean([s[1] for s in splits]):.2f} s/frame')
+    sample = (f'per step {n_sample} of {n_chunks} U-Net chunks timed (fp32 torch CPU, train-mode BN, {threads} threads) '
+              f'and EXTRAPOLATED x{n_chunks}/{n_sample}, plus the full post-U-Net stage (scipy/numpy + C heap flood, one '
+              f'thread like the numba original) on the NETWORK-derived feature volume of the same frame; mean U-Net '
+              f'{np.mean([s[0] for s in splits]):.2f} s/chunk, post {np.mean([s[1] for s in splits]):.2f} s/frame; one '
+              f'whole frame computed without extrapolation took {full_frame_s:.1f} s '
+              f'({nvox / full_frame_s:.0f} voxels/s)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'voxels/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -186,7 +195,8 @@ def run_reference(args, rank):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'frame': list(FRAME), 'chunk': list(CHUNK), 'margin': list(MARGIN)},
         'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                         'sample': sample},
+                         'sample': sample, 'extrapolated': True,
+                         'full_frame_s': full_frame_s, 'full_frame_voxels_per_s': nvox / full_frame_s},
         'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -197,7 +207,185 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+TC_KERNEL_LABEL = ('conv3d_tc_kernel x13 + conv3d_zring32_kernel x2 + conv3d_zring_kernel '
+                   '(the 16 TMA-fed tcgen05 implicit-GEMM launches per step)')
+
+
+def conv_traffic():
+    """DRAM bytes per TMA-fed conv launch (average over the 16 layers) from the committed
+    `ncu --set full` capture -- only when that capture was taken of the kernel set this binary
+    launches (the file names it); a stale capture gives (None, why)."""
+    fn = os.path.join(ROOT, 'profiles', 'r02_conv_traffic.json')
+    try:
+        with open(fn) as f:
+            d = json.load(f)
+    except Exception:
+        return None, 'profiles/r02_conv_traffic.json is missing'
+    if d.get('kernel_label') != TC_KERNEL_LABEL:
+        return None, ('profiles/r02_conv_traffic.json was captured for "%s", this binary launches "%s"'
+                      % (d.get('kernel_label'), TC_KERNEL_LABEL))
+    return float(d['dram_bytes_per_launch']), 'ncu --set full, ' + str(d.get('source', 'profiles/'))
+
+
+def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
+    """BASELINE.json configs[2]: ONE n_frames-frame tzyx series through the public frame loop
+    (`segmentation.segmentation_loop`, what `segment_data` runs), frames sharded t = rank (mod
+    world) when world > 1, global label ids from the per-step NCCL all-gather, every rank writing
+    its frames into ONE output store.  Fixed total work: strong scaling.  Timed by the host clock
+    between barriers (max over ranks): pinned host frames in, labels in the store out."""
+    import torch
+    import torch.distributed as dist
+    from iterseg_b200 import _io, distributed as idist, segmentation, synth
+    own = idist.shard_frames(n_frames, rank, world)
+    t0 = time.perf_counter()
+    data = synth.JitteredSeries(n_frames, FRAME, n_base=4, own=own, pin=True)
+    t_gen = time.perf_counter() - t0
+    nvox = float(np.prod(FRAME)) * n_frames
+    cfg = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'global_label_offsets': True}
+    rec = {'frames': n_frames, 'frames_per_rank': len(own), 'scaling': 'strong',
+           'api': 'segmentation.segmentation_loop (frames t = rank mod world, global label offsets by an NCCL '
+                  'all-gather per step, device-resident prefix)', 'synth_s': round(t_gen, 2)}
+
+    def timed(out):
+        barrier()
+        t0 = time.perf_counter()
+        done = list(segmentation.segmentation_loop(None, data, CHUNK, MARGIN, out,
+                                                   segmentation.affinity_watershed_for_chunks, cfg))
+        torch.cuda.synchronize()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert done == own, (done[:4], own[:4])
+        return float(dt.item())
+
+    # (a) every rank's frames into its own pinned (T_own) block of an in-memory array: no file I/O
+    mem = torch.zeros((n_frames,) + FRAME, dtype=torch.int32).pin_memory() if world == 1 else None
+    if mem is not None:
+        dt = timed(mem.numpy())
+        rec['in_memory'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3}
+        total = int(segmentation.LAST_COUNTS['global_total'].item())
+        rec['labels_total'] = total
+        rec['labels_global_ok'] = bool(int(mem[-1].max()) == total and int(mem[0].max()) < int(mem[-1].max()))
+        del mem
+    # (b) ONE OME-zarr label store shared by all ranks (save_dir of segment_data; chunks = chunk_size
+    #     on tzyx data = 10-frame t-chunks, segmentation.py:776-782)
+    store = os.path.join(save_root, 'series.ome.zarr')
+    if rank == 0:
+        arr = _io.save_labels_to_ome(store, layer_meta={'scale': (1, 4, 1, 1), 'translate': (0, 0, 0, 0),
+                                                        'name': 'series'},
+                                     shape=data.shape, chunks=CHUNK, dtype=np.int32)
+    barrier()
+    if rank != 0:
+        arr = _io.open_zarr(os.path.join(store, '0'), shape=data.shape, chunks=CHUNK, dtype=np.int32)
+    dt = timed(arr)
+    total = int(segmentation.LAST_COUNTS['global_total'].item())
+    rec['zarr'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3,
+                   'store': 'OME-zarr v0.4 labels, int32, chunks (10,33,256,512), raw chunks, /tmp'}
+    rec['labels_total'] = total
+    if rank == 0:
+        # frames of different ranks that share one t-chunk file, read back: non-empty, ids ascending
+        mx = [int(np.asarray(arr[t]).max()) for t in (0, 1, 9, n_frames - 1)]
+        rec['zarr_readback_max_label'] = mx
+        rec['zarr_ok'] = bool(mx[0] > 0 and mx[0] < mx[1] < mx[2] < mx[3] and mx[3] == total)
+    return rec
+
+
+def slab_record(net, rank, world, dev, barrier, shape=(256, 2048, 2048), halo=16, check_single=True):
+    """BASELINE.json configs[3]: ONE volume sharded into z-slabs with halo planes over the ranks
+    (iterseg_b200/slab.py), seam label merge by global seed keys.  Timed region (device events,
+    max over ranks): pinned host planes -> H2D -> U-Net of the own chunks -> halo exchange ->
+    all-reduced statistics -> post stage -> global relabel -> D2H of the own label planes."""
+    import torch
+    import torch.distributed as dist
+    from iterseg_b200 import slab as islab, synth, watershed as ws
+    slabs, _ = islab.plan_slabs(shape, CHUNK, MARGIN, world)
+    me = slabs[rank]
+    t0 = time.perf_counter()
+    host = torch.empty((me.in1 - me.in0,) + tuple(shape[1:]), dtype=torch.float32).pin_memory()
+    synth.big_volume_planes(shape, me.in0, me.in1, out=host.numpy())
+    t_gen = time.perf_counter() - t0
+
+    class Planes:                       # the rank-local window of the volume, indexed with global z
+        def __init__(self):
+            self.shape = tuple(shape)
+
+        def __getitem__(self, sl):
+            assert sl.start >= me.in0 and sl.stop <= me.in1
+            return host[sl.start - me.in0:sl.stop - me.in0]
+
+    vol = Planes()
+    out_host = torch.empty((me.z1 - me.z0,) + tuple(shape[1:]), dtype=torch.int32).pin_memory()
+    n_labels = None
+    times = []
+    for it in range(2):                 # warm-up (plans, workspaces, NCCL channels) + timed
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        own, (z0, z1), n_labels = islab.segment_volume_slabs(vol, net, CHUNK, MARGIN, halo=halo)
+        out_host.copy_(own, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    ms = times[-1]
+    nvox = float(np.prod(shape))
+    n_chunks = int(sum(len(s.chunks) for s in slabs))
+    rec = {'volume': list(shape), 'chunks': n_chunks, 'halo_planes': halo, 'slabs': [[s.z0, s.z1] for s in slabs],
+           'ms': ms, 'warmup_ms': times[0], 'voxels_per_s': nvox / (ms * 1e-3),
+           'chunks_per_s_per_gpu': n_chunks / world / (ms * 1e-3), 'labels': int(n_labels),
+           'synth_s': round(t_gen, 2),
+           'api': 'slab.segment_volume_slabs (also behind segmentation_loop for 3-D data under torch.distributed)'}
+    if not check_single:
+        return rec
+    # ---- the same volume on ONE device (rank 0), compared bit for bit with the ranks' own planes ----
+    ws._ws_cache.clear()
+    own_dev = own.contiguous()
+    del own
+    ref, err = None, None
+    if rank == 0:
+        try:
+            from iterseg_b200 import predict
+            full = torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
+            synth.big_volume_planes(shape, 0, shape[0], out=full.numpy())
+            t0 = time.perf_counter()
+            frame = full.to(dev, non_blocking=True)
+            frame = frame / frame.amax()
+            feats = predict.predict_frame_device(net, frame, CHUNK, MARGIN)
+            del frame
+            lab = torch.zeros(tuple(s + 2 for s in shape), dtype=torch.int32, device=dev)
+            nv = int(np.prod(shape))
+            ws.segment_features_device(feats, lab, max_flood_nodes=nv // 8)
+            torch.cuda.synchronize()
+            rec['single_device_s'] = time.perf_counter() - t0
+            del feats
+            ref = lab[1:-1, 1:-1, 1:-1]
+        except Exception as e:                                    # noqa: BLE001
+            err = repr(e)[:300]
+    box = [err is None and ref is not None]
+    dist.broadcast_object_list(box, src=0)                        # every rank learns whether to send its planes
+    if not box[0]:
+        rec['identical_to_single_device'] = None
+        rec['single_device_error'] = err
+        return rec
+    if rank == 0:
+        same = bool(torch.equal(ref[me.z0:me.z1], own_dev))
+        for r in range(1, world):
+            s = slabs[r]
+            b = torch.empty((s.z1 - s.z0,) + tuple(shape[1:]), dtype=torch.int32, device=dev)
+            dist.recv(b, src=r)
+            same = same and bool(torch.equal(ref[s.z0:s.z1], b))
+            del b
+        rec['identical_to_single_device'] = same
+        rec['single_device_labels'] = int(ref.max().item())
+    else:
+        dist.send(own_dev, dst=0)
+    return rec
+
+
 def run_gpu(args, rank, local_rank, world):
+    import tempfile
     import torch
     import torch.distributed as dist
     from iterseg_b200 import _lib, distributed as idist, predict, segmentation, synth, unet as unet_mod
@@ -215,7 +403,7 @@ def run_gpu(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- assets (untimed): synthetic frame of this rank, synthetic network file -----------
-    vol_np, lab_gt = synth.platelet_frame(FRAME, seed=rank, return_labels=True)
+    vol_np = synth.platelet_frame(FRAME, seed=rank)
     sd = synth.structured_state_dict(0)
     net = unet_mod.UNet()
     net.load_state_dict(sd)
@@ -224,38 +412,43 @@ def run_gpu(args, rank, local_rank, world):
     shape_p = tuple(s + 2 for s in FRAME)
     labels = torch.zeros(shape_p, dtype=torch.int32, device=dev)
     feats = torch.zeros((5,) + FRAME, dtype=torch.float32, device=dev)
+    crop = torch.zeros(FRAME, dtype=torch.int32, device=dev)
     nvox = float(np.prod(FRAME))
 
     from iterseg_b200.pipeline import FramePipeline
     pipe = FramePipeline(net, FRAME, CHUNK, MARGIN)
+    offsets = idist.LabelOffsets(rank, world, dev)
 
     def steps_device(k):
         """k complete frames (all kernels of every frame inside the call): the post stage of
-        frame i overlaps the U-Net of frame i+1 on a second stream (iterseg_b200/pipeline.py)."""
+        frame i overlaps the U-Net of frame i+1 on a second stream (iterseg_b200/pipeline.py);
+        with world > 1 the per-step all-gather of the label counts and the device-resident
+        offset (no host read-back) are part of every step."""
         counts = None
         pipe.submit(frame)
         for i in range(k):
             if i + 1 < k:
                 pipe.submit(frame)
             lab, counts = pipe.collect()
-            if world > 1:
-                with torch.cuda.stream(pipe.s_post):
-                    n_local = int(counts[0].item())
-                    all_counts = idist.gather_label_counts({rank: n_local}, world, rank, world, device=dev)
-                    idist.add_label_offset_(lab, int(idist.exclusive_offsets(all_counts)[rank]))
+            with torch.cuda.stream(pipe.s_post):
+                off = offsets.step(counts[0:1]) if world > 1 else None
+                _lib.check(lib.isg_crop_labels(lab.data_ptr(), FRAME[0], FRAME[1], FRAME[2], crop.data_ptr(),
+                                               off.data_ptr() if off is not None else None,
+                                               _lib.stream_ptr()), 'isg_crop_labels')
         pipe.drain_to()
         return counts
 
     # pinned host buffers for the end-to-end (public API) measurement: a K-frame tzyx series
     # through `segmentation.segmentation_loop`, the frame loop behind `segment_data` /
-    # `affinity_unet_watershed` (labels restart at 1 in every frame, as in the reference)
-    n_e2e = max(args.steps, 2)
+    # `affinity_unet_watershed`; with world > 1 every rank runs its own K frames (weak scaling,
+    # like `value`) and the label ids are made global by the per-step all-gather
+    n_e2e = max(args.steps, 4)
     series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
     out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
-    config = {'unet': net, 'output_volume': np.zeros((1,), np.float32)}
+    config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False}
 
-    def run_e2e():
-        out = out_series.numpy()
+    def run_e2e(out=None):
+        out = out_series.numpy() if out is None else out
         out[...] = 0                       # untimed: the caller's fresh output store
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -269,7 +462,7 @@ def run_gpu(args, rank, local_rank, world):
     sampler.start()                       # before the warm-up: nvidia-smi needs ~0.2 s to come up
     counts = steps_device(max(args.warmup, 1))
     barrier()
-    plan = list(net._plans.values())[0]
+    plan = list(net._plans.values())[-1]
     _lib.check(lib.isg_unet_plan_profile(plan.ptr, 1), 'profile')
     launches0 = lib.isg_launch_count()
     sampler.mark()
@@ -291,6 +484,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = nvox * world / (ms_step * 1e-3)
+    labels_device_run = crop.cpu().numpy() if world == 1 else None
 
     # ---- end to end through the public frame loop, host buffers ---------------------------------
     run_e2e()                                   # warm-up
@@ -303,7 +497,32 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = nvox * world * n_e2e / float(t.item())
-    e2e_labels_ok = bool(int(out_series[0].max()) == int(counts[0].item()) or world > 1)
+    # the labels the public loop wrote for frame 0 == the labels of the device-resident run
+    e2e_labels_ok = bool(np.array_equal(out_series[0].numpy(), labels_device_run)) if world == 1 else None
+
+    save_root = tempfile.mkdtemp(prefix='isg_bench_') if rank == 0 else None
+    if world > 1:
+        box = [save_root]
+        dist.broadcast_object_list(box, src=0)
+        save_root = box[0]
+    # e2e with save_dir semantics: the same K-frame loop writing an OME-zarr label store (N = 1)
+    e2e_zarr = None
+    if world == 1:
+        from iterseg_b200 import _io
+        arr = _io.save_labels_to_ome(os.path.join(save_root, 'e2e.ome.zarr'),
+                                     layer_meta={'scale': (1, 4, 1, 1), 'translate': (0, 0, 0, 0), 'name': 'e2e'},
+                                     shape=(n_e2e,) + FRAME, chunks=CHUNK, dtype=np.int32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done = list(segmentation.segmentation_loop(None, series.numpy(), CHUNK, MARGIN, arr,
+                                                   segmentation.affinity_watershed_for_chunks, config))
+        torch.cuda.synchronize()
+        dtz = time.perf_counter() - t0
+        e2e_zarr = {'value': nvox * n_e2e / dtz, 'unit': 'voxels/s', 's': dtz,
+                    'store': 'OME-zarr v0.4 label store under /tmp (save_dir of segment_data), int32 raw chunks',
+                    'readback_equals_in_memory_run': bool(np.array_equal(np.asarray(arr[n_e2e - 1]),
+                                                                         out_series[n_e2e - 1].numpy()))}
+        del arr
 
     # ---- post stage alone (not overlapped), device-timed: the HBM-side roofline entry -----------
     post_ms = None
@@ -319,11 +538,37 @@ def run_gpu(args, rank, local_rank, world):
         p1.record()
         torch.cuda.synchronize()
         post_ms = p0.elapsed_time(p1) / reps
+    feats_host = feats.cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    # ---- configs[2] / configs[3] records ----------------------------------------------------------
+    del series, out_series
+    series_rec = slab_rec = None
+    if not args.no_series:
+        try:
+            series_rec = series_record(net, rank, world, dev, barrier, save_root, n_frames=args.series_frames)
+        except Exception as e:                                    # noqa: BLE001
+            series_rec = {'error': repr(e)[:300]}
+    if world > 1 and not args.no_slab:
+        del pipe, feats, labels
+        ws._ws_cache.clear()
+        torch.cuda.empty_cache()
+        try:
+            slab_rec = slab_record(net, rank, world, dev, barrier, shape=tuple(args.slab_shape),
+                                   halo=args.slab_halo, check_single=not args.no_slab_check)
+        except Exception as e:                                    # noqa: BLE001
+            slab_rec = {'error': repr(e)[:300]}
+    if rank == 0:
+        import shutil
+        shutil.rmtree(save_root, ignore_errors=True)
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
         ach_tf = (tc_flops * n_fw) / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         counts_h = [int(x) for x in counts.cpu().numpy()]
+        traffic, traffic_src = conv_traffic()
+        unet_ms = fw_ms / n_fw if n_fw else None
+        unet_flops = float(plan.flops)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'voxels/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -343,18 +588,28 @@ def run_gpu(args, rank, local_rank, world):
                     'h2d_bytes_per_step': int(np.prod(FRAME) * 4) * world,
                     'd2h_bytes_per_step': int(np.prod(FRAME) * 4) * world,
                     'api': f'segmentation.segmentation_loop over a pinned {n_e2e}-frame tzyx series (the frame loop '
-                           f'of segment_data): per frame H2D, min/max + normalise, U-Net, post stage, D2H into the '
-                           f'caller\'s int32 array; two frames in flight; median of 3 timed runs',
-                    'runs_s': [round(x, 5) for x in e2e_runs], 'labels_match_device_run': e2e_labels_ok},
+                           f'of segment_data): loader threads, H2D + min/max on a copy stream, normalise + U-Net, '
+                           f'post stage, crop, one contiguous D2H per frame into the caller\'s pinned int32 array; '
+                           f'no host wait on a compute stream; median of 3 timed runs',
+                    'runs_s': [round(x, 5) for x in e2e_runs], 'labels_equal_device_run': e2e_labels_ok,
+                    'vs_value': e2e_value / value},
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': ach_tf / peak_tf if peak_tf else None, 'traffic': conv_traffic(),
-                         'kernel': 'conv3d_tc_kernel x13 + conv3d_zring32_kernel x2 + conv3d_zring_kernel (the 16 TMA-fed tcgen05 implicit-GEMM launches per step)',
+                         'frac': ach_tf / peak_tf if peak_tf else None, 'traffic': traffic,
+                         'traffic_source': traffic_src,
+                         'kernel': TC_KERNEL_LABEL,
                          'peak_source': f'{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)',
                          'share_of_step': (tc_ms / n_fw) / ms_step if n_fw else None,
-                         'unet_ms_per_step': fw_ms / n_fw if n_fw else None},
+                         'unet_ms_per_step': unet_ms,
+                         'unet_whole_network': {
+                             'tflops': unet_flops / (unet_ms * 1e-3) / 1e12 if unet_ms else None,
+                             'frac_sustained': unet_flops / (unet_ms * 1e-3) / 1e12 / peak_tf if unet_ms else None,
+                             'frac_burst': (unet_flops / (unet_ms * 1e-3) / 1e12 / float(peaks['bf16_tflops'])
+                                            if unet_ms and peaks.get('bf16_tflops') else None)}},
         }
+        if e2e_zarr is not None:
+            line['e2e_zarr'] = e2e_zarr
         hbm = float(peaks.get('hbm_gbs_sustained', peaks.get('hbm_gbs', 6650.0)))
         post_bytes = 24.0 * nvox              # 5 x f32 feature reads + 1 x u32 label write per voxel
         line['roofline_post'] = {
@@ -363,17 +618,30 @@ def run_gpu(args, rank, local_rank, world):
             'kernel': 'post-U-Net stage (seeds, Otsu mask, components, ordered flood), timed alone',
             'ms': post_ms,
             'note': 'latency bound, not HBM bound: the order-exact flood of the largest multi-seed object '
-                    '(one warp, ~660 clk per voxel) sets the time; see profiles/r01_notes.md'}
+                    '(one warp per object) sets the time; see profiles/r02_notes.md'}
+        if series_rec is not None:
+            line['series'] = series_rec
+        if slab_rec is not None:
+            line['slab'] = slab_rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            per_frame, t_unet, t_post, n_chunks = cpu_reference_step(vol_np, lab_gt, sd, 3, threads)
+            from oracle import chunks as ochunks, flood as oflood
+            oflood.build()
+            starts, _ = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
+            pick = [starts[i] for i in np.linspace(0, len(starts) - 1, 3).astype(int)]
+            t_unet, _ = cpu_unet_chunks(vol_np, sd, pick, threads)
+            t_post, lab_cpu = cpu_post(feats_host)
+            per_frame = t_unet * len(starts) + t_post
             line['cpu_baseline'] = {
-                'value': nvox / per_frame, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                'sample': (f'3 of {n_chunks} U-Net chunks timed on {threads} threads ({t_unet:.2f} s/chunk, fp32 '
-                           f'torch CPU, train-mode BN) extrapolated to {n_chunks}; full post-U-Net stage '
-                           f'({t_post:.2f} s, single thread) on analytic feature maps of the same frame')}
+                'value': nvox / per_frame, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port', 'extrapolated': True,
+                'sample': (f'3 of {len(starts)} U-Net chunks timed on {threads} threads ({t_unet:.2f} s/chunk, fp32 '
+                           f'torch CPU, train-mode BN) extrapolated to {len(starts)}; full post-U-Net stage '
+                           f'({t_post:.2f} s, single thread) on the SAME network-derived feature volume the GPU '
+                           f'post stage ran on'),
+                'post_labels_equal_gpu': bool(np.array_equal(lab_cpu, labels.cpu().numpy().view(np.uint32)))}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -490,6 +758,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-series', action='store_true', help='skip the configs[2] 192-frame series record')
+    ap.add_argument('--series-frames', type=int, default=192)
+    ap.add_argument('--no-slab', action='store_true', help='skip the configs[3] slab record (N > 1 only)')
+    ap.add_argument('--no-slab-check', action='store_true',
+                    help='skip the single-device run the slab labels are compared with')
+    ap.add_argument('--slab-shape', type=int, nargs=3, default=[256, 2048, 2048])
+    ap.add_argument('--slab-halo', type=int, default=16)
     ap.add_argument('--segmenter', default='affinity', choices=['affinity', 'dog'],
                     help="'dog': the DoG blob watershed (BASELINE.json configs[4]) instead of the headline path")
     args = ap.parse_args()

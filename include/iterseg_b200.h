@@ -133,6 +133,14 @@ typedef struct {
 } isg_post_params;
 
 size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds);
+/* isg_post_workspace_bytes covers the worst case -- every voxel inside a multi-seed mask
+ * component (about 200 bytes per voxel).  isg_segment_features also accepts a SMALLER workspace:
+ * whatever lies beyond the fixed part becomes the compact node / edge arenas of the ordered flood,
+ * and a frame whose multi-seed components do not fit fails with ISG_ERR_WORKSPACE (nothing is
+ * silently dropped).  This query sizes a workspace for at most `max_flood_nodes` such voxels --
+ * what the z-slab path uses, where a slab of 2048 x 2048 planes would otherwise need > 60 GB. */
+size_t isg_post_workspace_bytes_capped(int64_t z, int64_t y, int64_t x, int64_t max_seeds,
+                                       int64_t max_flood_nodes);
 int isg_segment_features(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
                          const isg_post_params *params,
                          const double *gauss1_host, const double *gauss2_host,
@@ -224,7 +232,16 @@ int isg_unet_weights_pack(const void *const *tensors, int n_tensors, void *packe
 
 size_t isg_unet_workspace_bytes(int n_chunks, int cz, int cy, int cx);
 /* chunk tables are HOST arrays of n_chunks*3 int32: start (z,y,x), crop_lo, crop_hi
- * exactly as make_chunks returns them (predict.py:38-61). */
+ * exactly as make_chunks returns them (predict.py:38-61).  They may be NULL at creation and
+ * (re)set at any time with isg_unet_plan_set_chunks: a plan is a (frame extent, chunk extent,
+ * chunk count) geometry over a workspace, the tables are per-call data.  The tables are copied
+ * into pinned memory owned by the plan and uploaded by the NEXT isg_unet_forward_chunks with
+ * cudaMemcpyAsync on that call's stream -- no blocking copy, nothing on the legacy stream.
+ * Several plans may share one workspace as long as their forward passes are enqueued on the
+ * same stream (or otherwise ordered): a forward pass leaves nothing in the workspace that a
+ * later one needs. */
+int isg_unet_plan_set_chunks(isg_unet_plan *plan, const int32_t *starts_host,
+                             const int32_t *crop_lo_host, const int32_t *crop_hi_host);
 isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n_chunks,
                                     int cz, int cy, int cx,
                                     int64_t z, int64_t y, int64_t x,
@@ -235,6 +252,17 @@ void isg_unet_plan_destroy(isg_unet_plan *plan);
 /* frame (Z,Y,X) float32 -> feats (5,Z,Y,X) float32: every voxel written by exactly
  * one chunk's cropped interior (predict.py:89-95). */
 int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream);
+/* fp16 range guard.  Filters are divided by a per-output-channel power of two at pack time (the
+ * train-mode BatchNorm that follows every convolution cancels it; BN_EPS is rescaled to match), so
+ * the fp16 weights and pre-BatchNorm activations stay O(1) for any filter scale.  Should an
+ * activation still leave the fp16 range (|x| >= ~5.6e3 counts), the kernels raise a sticky device
+ * flag that every forward pass copies to pinned host memory:
+ *   isg_unet_plan_overflowed   != 0 iff a forward pass of this plan that has COMPLETED overflowed
+ *                              (no synchronisation: call it after waiting for the features);
+ *                              isg_unet_forward_chunks then refuses with ISG_ERR_OVERFLOW
+ *   isg_unet_plan_clear_overflow   re-arms the flag (stream-ordered). */
+int isg_unet_plan_overflowed(const isg_unet_plan *plan);
+int isg_unet_plan_clear_overflow(isg_unet_plan *plan, void *stream);
 /* debugging / parity: run the network on `frame` up to and including the convolution
  * `name` ("c0.conv0" ... "c8_0.conv1") and return its raw (pre-BatchNorm, bias-free)
  * output for chunk `chunk` as fp32 NCDHW (out_elems = Cout*D*H*W of that level). */
@@ -255,6 +283,12 @@ int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out);
  * an addition of this implementation, the reference restarts at 1 in every frame,
  * watershed.py:61-62). */
 int isg_add_label_offset(uint32_t *labels, int64_t n, uint32_t offset, void *stream);
+/* The crop the driver applies to the padded output (segmentation.py:896,900) on the device:
+ * labels_padded (z+2,y+2,x+2) -> out (z,y,x) contiguous, ready for ONE contiguous device->host copy.
+ * offset_dev: NULL, or a device int64 added to every non-zero label (the running global label
+ * offset of a frame-sharded series stays on the device: no host round trip per frame). */
+int isg_crop_labels(const uint32_t *labels_padded, int64_t z, int64_t y, int64_t x, uint32_t *out,
+                    const int64_t *offset_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,34 +45,87 @@ class LabelArray:
     """Chunked integer array: zarr-v2 directory store (path given) or in memory."""
 
     def __init__(self, shape, chunks, dtype=np.int32, path=None):
+        self.path = None if path is None else str(path)
+        self._mem = None
+        self.sep = '.'
+        meta_fn = None if self.path is None else os.path.join(self.path, '.zarray')
+        if meta_fn is not None and os.path.exists(meta_fn):
+            # an existing store is re-opened with ITS OWN metadata, like zarr.open(mode='a') in the
+            # reference's open_zarr (_io.py:325-386): a warm restart must find the frames where
+            # the first run put them, whatever chunk_size this call was given
+            with open(meta_fn) as f:
+                meta = json.load(f)
+            if meta.get('zarr_format') != 2:
+                raise NotImplementedError(f'{self.path}: only zarr format 2 stores are supported')
+            if meta.get('compressor') is not None or meta.get('filters'):
+                raise NotImplementedError(
+                    f'{self.path} was written with compressor {meta.get("compressor")!r} / filters '
+                    f'{meta.get("filters")!r}: this writer reads and writes raw (uncompressed) chunks only; '
+                    'resume with the tool that created the store or start a fresh one')
+            if meta.get('order', 'C') != 'C':
+                raise NotImplementedError(f'{self.path}: only C-order chunks are supported')
+            if shape is not None and tuple(int(v) for v in shape) != tuple(meta['shape']):
+                raise ValueError(f'{self.path} holds an array of shape {tuple(meta["shape"])}, '
+                                 f'not the requested {tuple(shape)}')
+            self.shape = tuple(int(v) for v in meta['shape'])
+            self.chunks = tuple(int(v) for v in meta['chunks'])
+            self.dtype = np.dtype(meta['dtype'])
+            self.sep = meta.get('dimension_separator', '.')
+            self.ndim = len(self.shape)
+            return
         self.shape = tuple(int(s) for s in shape)
         self.chunks = normalize_chunks(chunks, self.shape)
         self.dtype = np.dtype(dtype)
         self.ndim = len(self.shape)
-        self.path = None if path is None else str(path)
-        self._mem = None
         if self.path is None:
             self._mem = np.zeros(self.shape, dtype=self.dtype)
         else:
             os.makedirs(self.path, exist_ok=True)
-            meta_fn = os.path.join(self.path, '.zarray')
-            if not os.path.exists(meta_fn):
-                meta = {'zarr_format': 2, 'shape': list(self.shape), 'chunks': list(self.chunks),
-                        'dtype': self.dtype.newbyteorder('<').str, 'compressor': None,
-                        'fill_value': 0, 'order': 'C', 'filters': None,
-                        'dimension_separator': '.'}
-                with open(meta_fn, 'w') as f:
-                    json.dump(meta, f, indent=1)
+            meta = {'zarr_format': 2, 'shape': list(self.shape), 'chunks': list(self.chunks),
+                    'dtype': self.dtype.newbyteorder('<').str, 'compressor': None,
+                    'fill_value': 0, 'order': 'C', 'filters': None,
+                    'dimension_separator': '.'}
+            tmp = meta_fn + f'.tmp{os.getpid()}'
+            with open(tmp, 'w') as f:
+                json.dump(meta, f, indent=1)
+            os.replace(tmp, meta_fn)                     # atomic: several ranks may create the same store
 
     # ---- chunk files ----------------------------------------------------------
     def _chunk_fn(self, idx):
-        return os.path.join(self.path, '.'.join(str(i) for i in idx))
+        fn = os.path.join(self.path, self.sep.join(str(i) for i in idx))
+        if self.sep == '/':
+            os.makedirs(os.path.dirname(fn), exist_ok=True)
+        return fn
 
     def _read_chunk(self, idx):
         fn = self._chunk_fn(idx)
         if not os.path.exists(fn):
             return np.zeros(self.chunks, dtype=self.dtype)
-        return np.fromfile(fn, dtype=self.dtype.newbyteorder('<')).reshape(self.chunks)
+        a = np.fromfile(fn, dtype=self.dtype.newbyteorder('<'))
+        n = int(np.prod(self.chunks))
+        if a.size < n:                                   # a chunk file that is still being extended
+            a = np.concatenate([a, np.zeros(n - a.size, dtype=a.dtype)])
+        return a[:n].reshape(self.chunks)
+
+    def _update_chunk(self, idx, src, block):
+        """Write `block` into region `src` of chunk `idx` IN PLACE (no read-modify-write of the
+        whole chunk file): raw C-order chunks have a fixed byte layout, so the region is stored
+        through a shared mapping of the file.  Processes that write DISJOINT regions of one chunk
+        file (ranks that own different frames of a t-chunk, distributed.shard_frames) never
+        touch each other's bytes; a file that does not exist yet is created sparse, its holes
+        read as the fill value 0."""
+        fn = self._chunk_fn(idx)
+        nbytes = int(np.prod(self.chunks)) * self.dtype.itemsize
+        fd = os.open(fn, os.O_RDWR | os.O_CREAT, 0o644)
+        try:
+            if os.fstat(fd).st_size < nbytes:
+                os.ftruncate(fd, nbytes)                 # extending keeps what other writers stored
+        finally:
+            os.close(fd)
+        mm = np.memmap(fn, dtype=self.dtype.newbyteorder('<'), mode='r+', shape=self.chunks)
+        mm[src] = block
+        mm.flush()
+        del mm
 
     def _norm_key(self, key):
         if not isinstance(key, tuple):
@@ -100,8 +153,19 @@ class LabelArray:
             return self._mem[key]
         rng, squeeze = self._norm_key(key)
         res = np.zeros([b - a for a, b in rng], dtype=self.dtype)
+        n_chunk = int(np.prod(self.chunks))
         for idx, src, dst in self._overlaps(rng):
-            res[dst] = self._read_chunk(idx)[src]
+            fn = self._chunk_fn(idx)
+            if not os.path.exists(fn):
+                continue                                 # fill value 0
+            if os.path.getsize(fn) >= n_chunk * self.dtype.itemsize:
+                # only the pages of the requested region are read (a t-chunk of the reference's
+                # chunks=chunk_size layout holds 10 frames, segmentation.py:776-782)
+                mm = np.memmap(fn, dtype=self.dtype.newbyteorder('<'), mode='r', shape=self.chunks)
+                res[dst] = mm[src]
+                del mm
+            else:
+                res[dst] = self._read_chunk(idx)[src]
         return res.reshape([n for n, sq in zip(res.shape, squeeze) if not sq])
 
     def __setitem__(self, key, value):
@@ -114,9 +178,11 @@ class LabelArray:
         value = np.broadcast_to(np.asarray(value).astype(self.dtype, copy=False), kept).reshape(full)
         for idx, src, dst in self._overlaps(rng):
             whole = all(s.start == 0 and s.stop == c for s, c in zip(src, self.chunks))
-            chunk = np.empty(self.chunks, dtype=self.dtype) if whole else self._read_chunk(idx)
-            chunk[src] = value[dst]
-            chunk.astype(self.dtype.newbyteorder('<'), copy=False).tofile(self._chunk_fn(idx))
+            if whole:
+                np.ascontiguousarray(value[dst]).astype(self.dtype.newbyteorder('<'), copy=False) \
+                    .tofile(self._chunk_fn(idx))
+            else:
+                self._update_chunk(idx, src, value[dst])
 
     def _overlaps(self, rng):
         import itertools
@@ -140,6 +206,8 @@ class LabelArray:
 
 
 def open_zarr(path, *, shape=None, chunks=None, dtype=None, **kwargs):
+    """_io.py:325-386: open (mode 'a') the array store at `path`; an existing store keeps its own
+    shape / chunks / dtype (shape is checked when given)."""
     return LabelArray(shape, chunks, dtype=dtype if dtype is not None else np.int32, path=path)
 
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     'isg_affinity_flood': (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                   _vp, _vp, _sz, _vp]),
     'isg_post_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
+    'isg_post_workspace_bytes_capped': (_sz, [_i64, _i64, _i64, _i64, _i64]),
     'isg_segment_features': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _vp,
                                     _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     'isg_slab_stats': (_i32, [_vp, _i32, _i64, _i64, _i64, _c.POINTER(PostParams), _vp, _i32, _vp, _vp, _vp,
@@ -57,20 +58,27 @@ SIGNATURES = {
     'isg_unet_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32]),
     'isg_unet_plan_create': (_vp, [_vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
                                    _vp, _sz]),
+    'isg_unet_plan_set_chunks': (_i32, [_vp, _vp, _vp, _vp]),
     'isg_unet_plan_destroy': (None, [_vp]),
+    'isg_unet_plan_overflowed': (_i32, [_vp]),
+    'isg_unet_plan_clear_overflow': (_i32, [_vp, _vp]),
     'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),
     'isg_unet_debug_activation': (_i32, [_vp, _vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
     'isg_unet_plan_flops': (_c.c_double, [_vp]),
     'isg_unet_plan_profile': (_i32, [_vp, _i32]),
     'isg_unet_plan_profile_read': (_i32, [_vp, _vp]),
     'isg_add_label_offset': (_i32, [_vp, _i64, _c.c_uint32, _vp]),
+    'isg_crop_labels': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None
 
 
 class IsgError(RuntimeError):
-    pass
+    status = None            # the C-ABI status code (ISG_ERR_*) when the error came from the library
+
+
+ISG_ERR_CUDA, ISG_ERR_ARG, ISG_ERR_WORKSPACE, ISG_ERR_OVERFLOW, ISG_ERR_DEVICE = 1, 2, 3, 4, 5
 
 
 def load():
@@ -94,7 +102,9 @@ def load():
 def check(rc, what=''):
     if rc != 0:
         msg = load().isg_last_error().decode('utf-8', 'replace')
-        raise IsgError(f'{what} failed (status {rc}): {msg}')
+        err = IsgError(f'{what} failed (status {rc}): {msg}')
+        err.status = int(rc)
+        raise err
 
 
 def require_device():

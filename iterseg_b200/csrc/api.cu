@@ -74,6 +74,24 @@ frame_minmax_kernel(const float *__restrict__ v, uint64_t n, uint32_t *__restric
         atomicMax(mm + 1, hi);
     }
 }
+__global__ void minmax_init_kernel(uint32_t *mm) {
+    mm[0] = 0xFFFFFFFFu;
+    mm[1] = 0u;
+}
+// padded (Z+2,Y+2,X+2) labels -> the (Z,Y,X) interior, contiguous (segmentation.py:896,900), with an
+// optional device-resident offset added to every non-zero label (frame-sharded series)
+__global__ void __launch_bounds__(256)
+crop_labels_kernel(const uint32_t *__restrict__ lab, int Z, int Y, int X, uint32_t *__restrict__ out,
+                   const long long *__restrict__ offset) {
+    const uint32_t off = offset ? (uint32_t)*offset : 0u;
+    const uint64_t n = (uint64_t)Z * Y * X, stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t yp = (uint64_t)Y + 2, xp = (uint64_t)X + 2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t x = i % X, t = i / X, y = t % Y, z = t / Y;
+        const uint32_t l = lab[((z + 1) * yp + (y + 1)) * xp + (x + 1)];
+        out[i] = l ? l + off : 0u;
+    }
+}
 __global__ void minmax_out_kernel(const uint32_t *__restrict__ mm, float *__restrict__ out) {
     out[0] = ord_f32(mm[0]);
     out[1] = ord_f32(mm[1]);
@@ -93,8 +111,8 @@ extern "C" int isg_frame_minmax(const float *frame, int64_t n, float *minmax_out
     ISG_REQUIRE(scratch_bytes >= 8, ISG_ERR_WORKSPACE, "isg_frame_minmax: scratch must hold 8 bytes");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *mm = reinterpret_cast<uint32_t *>(scratch);
-    const uint32_t init[2] = {0xFFFFFFFFu, 0u};
-    ISG_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    isg::minmax_init_kernel<<<1, 1, 0, st>>>(mm);       // (a copy from pageable host memory would stage synchronously)
+    ISG_LAUNCHED();
     isg::frame_minmax_kernel<<<isg::num_sms() * 8, 256, 0, st>>>(frame, (uint64_t)n, mm);
     ISG_LAUNCHED();
     isg::minmax_out_kernel<<<1, 1, 0, st>>>(mm, minmax_out);
@@ -113,6 +131,16 @@ extern "C" int isg_add_label_offset(uint32_t *labels, int64_t n, uint32_t offset
     ISG_REQUIRE(labels && n >= 0, ISG_ERR_ARG, "isg_add_label_offset: bad argument");
     if (n == 0 || offset == 0) return ISG_OK;
     isg::add_label_offset_kernel<<<isg::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(labels, (uint64_t)n, offset);
+    ISG_LAUNCHED();
+    return ISG_OK;
+}
+
+extern "C" int isg_crop_labels(const uint32_t *labels_padded, int64_t z, int64_t y, int64_t x, uint32_t *out,
+                               const int64_t *offset_dev, void *stream) {
+    ISG_REQUIRE(labels_padded && out && z > 0 && y > 0 && x > 0, ISG_ERR_ARG, "isg_crop_labels: bad argument");
+    ISG_REQUIRE(z < (1ll << 30) && y < (1ll << 30) && x < (1ll << 30), ISG_ERR_ARG, "isg_crop_labels: extent too large");
+    isg::crop_labels_kernel<<<isg::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(
+        labels_padded, (int)z, (int)y, (int)x, out, reinterpret_cast<const long long *>(offset_dev));
     ISG_LAUNCHED();
     return ISG_OK;
 }

@@ -263,7 +263,7 @@ static void dog_carve(DogBuffers *b, Carver &cv, uint64_t np, int64_t max_seeds)
     cub::DeviceScan::ExclusiveSum(nullptr, s2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(np + 1));
     b->cub_bytes = (s1 > s2 ? s1 : s2) + 256;
     b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
-    flood_stage_workspace(&b->flood, cv, np, max_seeds);
+    flood_stage_workspace(&b->flood, cv, np, max_seeds, np);
 }
 
 // 3-axis Gaussian in -> out using tmp (in is preserved)

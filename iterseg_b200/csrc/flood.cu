@@ -66,7 +66,8 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
                   uint32_t *__restrict__ comp_start, uint64_t *__restrict__ arena_off,
                   uint32_t *__restrict__ cbase, uint32_t *__restrict__ ebase,
                   uint32_t *__restrict__ scalars, uint32_t *__restrict__ order_keys,
-                  uint32_t *__restrict__ order_vals) {
+                  uint32_t *__restrict__ order_vals, uint64_t node_cap, uint64_t edge_cap,
+                  uint64_t arena_cap) {
     typedef cub::BlockScan<uint32_t, 1024> Scan32;
     typedef cub::BlockScan<uint64_t, 1024> Scan64;
     __shared__ union {
@@ -174,6 +175,15 @@ comp_group_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
         scalars[1] = acc;
         scalars[12] = carry32;
         scalars[13] = carry_e;
+        // The compact node / edge / heap arenas may be smaller than the worst case (a caller that
+        // knows its mask is sparse passes a smaller workspace): when the multi-seed components do
+        // not fit, nothing is flooded -- the work lists are emptied, the compaction kernels see
+        // scalars[14] and return, and the host reports ISG_ERR_WORKSPACE after its read-back.
+        if ((uint64_t)carry32 > node_cap || (uint64_t)carry_e > edge_cap || carry64 > arena_cap) {
+            scalars[14] = 1;
+            for (int k = 1; k < 10; ++k) scalars[k] = 0;
+            scalars[12] = 0;
+        }
     }
     for (uint32_t c = n_comp + t; c <= n; c += 1024) {     // padding up to the host-side count
         if (c < n) {
@@ -200,8 +210,12 @@ int ccl_run(const uint8_t *dom, uint32_t *parent, uint32_t *comp_size, uint32_t 
     return ISG_OK;
 }
 
-size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds) {
+size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds,
+                             uint64_t node_cap) {
     if (max_seeds < 1) max_seeds = 1;
+    if (node_cap > npix) node_cap = npix;
+    if (node_cap < 1) node_cap = 1;
+    b->node_cap = node_cap;
     b->keys_a = cv.take<uint64_t>(max_seeds);
     b->keys_b = cv.take<uint64_t>(max_seeds);
     b->vals_a = cv.take<uint32_t>(max_seeds);
@@ -222,19 +236,19 @@ size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, in
     b->cub_bytes = cub_bytes + 256;
     b->cub_tmp = cv.take<unsigned char>(b->cub_bytes);
     // heap arena (class XL): every domain voxel enters a heap at most once, plus the seeds
-    b->arena_cap = npix + (uint64_t)max_seeds;
+    b->arena_cap = node_cap + (uint64_t)max_seeds;
     b->arena_keys = cv.take<uint64_t>(b->arena_cap);
     b->arena_idx = cv.take<uint32_t>(b->arena_cap);
     // compact component graphs: at most one node per voxel
     b->lidmap = cv.take<uint32_t>(npix);
-    b->vox = cv.take<uint32_t>(npix);
-    b->nbr = cv.take<uint32_t>(npix * 6);
-    b->key = cv.take<uint32_t>(npix * 3);
-    b->nlab = cv.take<uint32_t>(npix);
-    b->rec = cv.take<uint4>(npix * 2);
+    b->vox = cv.take<uint32_t>(node_cap);
+    b->nbr = cv.take<uint32_t>(node_cap * 6);
+    b->key = cv.take<uint32_t>(node_cap * 3);
+    b->nlab = cv.take<uint32_t>(node_cap);
+    b->rec = cv.take<uint4>(node_cap * 2);
     // edge arena of the bucket-queue classes: 3 stored edges per node + one entry per seed
     b->ebase = cv.take<uint32_t>(max_seeds + 1);
-    b->edge_cap = npix * 3 + (uint64_t)max_seeds;
+    b->edge_cap = node_cap * 3 + (uint64_t)max_seeds;
     b->ekeys_a = cv.take<uint64_t>(b->edge_cap);
     b->ekeys_b = cv.take<uint64_t>(b->edge_cap);
     b->evals_a = cv.take<uint32_t>(b->edge_cap);
@@ -299,7 +313,8 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     count_launch(4);
     comp_group_kernel<<<1, 1024, 0, st>>>(b.keys_b, b.vals_b, (uint32_t)n_seeds, comp_size,
                                           comp_label, b.comp_start, b.arena_off, b.cbase, b.ebase,
-                                          b.scalars, b.order_keys_a, b.order_a);
+                                          b.scalars, b.order_keys_a, b.order_a, b.node_cap, b.edge_cap,
+                                          b.arena_cap);
     ISG_LAUNCHED();
     {
         size_t cb = b.cub_bytes;      // sized for 64-bit keys + 32-bit values: enough for 32/32
@@ -309,10 +324,10 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     }
     const int sms = num_sms();
     fill_assign_kernel<<<sms * 8, 256, 0, st>>>(parent, comp_label, mask, labels, b.cbase, b.ccursor,
-                                                b.lidmap, b.vox, npix);
+                                                b.lidmap, b.vox, npix, b.scalars + 14);
     ISG_LAUNCHED();
     seed_edge_kernel<<<blocks, 256, 0, st>>>(b.keys_b, (uint32_t)n_seeds, comp_label, b.comp_start,
-                                             b.ebase, b.ekeys_a, b.evals_a, geom.node_key);
+                                             b.ebase, b.ekeys_a, b.evals_a, geom.node_key, b.scalars + 14);
     ISG_LAUNCHED();
     compact_graph_kernel<<<sms * 8, 256, 0, st>>>(geom, parent, comp_label, b.comp_start, b.cbase, b.ebase,
                                                   b.lidmap, b.vox, b.scalars + 12, b.nbr, b.key, b.nlab,
@@ -324,9 +339,13 @@ int flood_stage_run(const FloodStageBuffers &b, const FloodGeom &geom, const uin
     cub::DoubleBuffer<uint64_t> dk(b.ekeys_a, b.ekeys_b);
     cub::DoubleBuffer<uint32_t> dv(b.evals_a, b.evals_b);
     {
-        uint32_t total_edges = 0;
-        ISG_CUDA(cudaMemcpyAsync(&total_edges, b.scalars + 13, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        uint32_t tail[2] = {0, 0};                        // scalars[13] = edge entries, [14] = arena overflow
+        ISG_CUDA(cudaMemcpyAsync(tail, b.scalars + 13, sizeof(tail), cudaMemcpyDeviceToHost, st));
         ISG_CUDA(cudaStreamSynchronize(st));
+        ISG_REQUIRE(tail[1] == 0, ISG_ERR_WORKSPACE,
+                    "flood stage: the multi-seed components need more than the %llu compact nodes this "
+                    "workspace holds (pass the full isg_*_workspace_bytes size)", (unsigned long long)b.node_cap);
+        const uint32_t total_edges = tail[0];
         ISG_REQUIRE((uint64_t)total_edges <= b.edge_cap, ISG_ERR_WORKSPACE, "flood stage: edge arena overflow");
         if (total_edges > 1) {
             int comp_bits = 1;
@@ -424,7 +443,7 @@ extern "C" size_t isg_flood_workspace_bytes(int64_t zp, int64_t yp, int64_t xp, 
     cv.take<uint32_t>(npix);       // comp_size
     cv.take<uint32_t>(npix);       // comp_label
     FloodStageBuffers b;
-    flood_stage_workspace(&b, cv, npix, max_seeds);
+    flood_stage_workspace(&b, cv, npix, max_seeds, npix);
     return cv.off + 512;
 }
 
@@ -448,7 +467,7 @@ extern "C" int isg_affinity_flood(const float *aff, int64_t aff_plane_stride, in
     uint32_t *comp_size = cv.take<uint32_t>(npix);
     uint32_t *comp_label = cv.take<uint32_t>(npix);
     FloodStageBuffers b;
-    flood_stage_workspace(&b, cv, npix, n_seeds);
+    flood_stage_workspace(&b, cv, npix, n_seeds, npix);
     ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE,
                 "isg_affinity_flood: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
     const int sms = num_sms();

@@ -582,9 +582,10 @@ __global__ void seed_edge_kernel(const uint64_t *__restrict__ seed_keys, uint32_
                                  const uint32_t *__restrict__ comp_label,
                                  const uint32_t *__restrict__ comp_start,
                                  const uint32_t *__restrict__ ebase, uint64_t *__restrict__ ekeys,
-                                 uint32_t *__restrict__ evals, const uint32_t *__restrict__ node_key) {
+                                 uint32_t *__restrict__ evals, const uint32_t *__restrict__ node_key,
+                                 const uint32_t *__restrict__ overflow) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || *overflow) return;
     const uint64_t k = seed_keys[i];
     if (k == ~0ull) return;
     const uint32_t cl = comp_label[(uint32_t)(k >> 32)];
@@ -605,7 +606,9 @@ __global__ void __launch_bounds__(256)
 fill_assign_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ comp_label,
                    const uint8_t *__restrict__ mask, uint32_t *__restrict__ labels,
                    const uint32_t *__restrict__ cbase, uint32_t *__restrict__ ccursor,
-                   uint32_t *__restrict__ lidmap, uint32_t *__restrict__ vox, uint64_t n) {
+                   uint32_t *__restrict__ lidmap, uint32_t *__restrict__ vox, uint64_t n,
+                   const uint32_t *__restrict__ overflow) {
+    const bool no_compaction = *overflow != 0;          // arenas too small: single-seed fill only
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31;
     const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -617,7 +620,7 @@ fill_assign_kernel(const uint32_t *__restrict__ parent, const uint32_t *__restri
             if (r != CCL_NONE) {
                 const uint32_t cl = comp_label[r];
                 if (cl & MULTI_FLAG) {
-                    c = cl & ~MULTI_FLAG;
+                    if (!no_compaction) c = cl & ~MULTI_FLAG;
                 } else if (cl != 0 && mask[v] && labels[v] == 0) {
                     labels[v] = cl;
                 }

@@ -35,6 +35,7 @@ struct FloodStageBuffers {
     uint64_t *arena_keys;
     uint32_t *arena_idx;
     uint64_t arena_cap;
+    uint64_t node_cap;                                           // compact nodes the arenas hold (<= npix)
     uint32_t *lidmap, *vox, *key, *nbr, *nlab;                   // compact component graphs
     uint4 *rec;                                                  // bucket-queue node records
     uint32_t *ebase;                                             // edge-arena segment per component
@@ -52,7 +53,11 @@ struct FloodStageBuffers {
 int ccl_run(const uint8_t *dom, uint32_t *parent, uint32_t *comp_size, uint32_t zp, uint32_t yp,
             uint32_t xp, cudaStream_t st);
 
-size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds);
+// node_cap: how many voxels of multi-seed components the compact arenas can hold (clamped to
+// [1, npix]; npix = the worst case, every voxel).  A run that needs more fails with
+// ISG_ERR_WORKSPACE and leaves the multi-seed components unflooded.
+size_t flood_stage_workspace(FloodStageBuffers *b, Carver &cv, uint64_t npix, int64_t max_seeds,
+                             uint64_t node_cap);
 
 // parent: flattened CCL roots of the flood domain (CCL_NONE outside);
 // comp_size: voxels per root; comp_label: zeroed scratch indexed by root;

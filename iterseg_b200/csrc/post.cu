@@ -322,7 +322,7 @@ struct PostBuffers {
     FloodStageBuffers flood;
 };
 
-static void post_carve(PostBuffers *b, Carver &cv, uint64_t n, uint64_t np, int64_t max_seeds) {
+static void post_carve(PostBuffers *b, Carver &cv, uint64_t n, uint64_t np, int64_t max_seeds, uint64_t node_cap) {
     b->tmp_a = cv.take<float>(n);
     b->tmp_b = cv.take<float>(n);
     b->cand_a = cv.take<uint64_t>(max_seeds);
@@ -340,19 +340,44 @@ static void post_carve(PostBuffers *b, Carver &cv, uint64_t n, uint64_t np, int6
     b->parent = cv.take<uint32_t>(np);
     b->comp_size = cv.take<uint32_t>(np);
     b->comp_label = cv.take<uint32_t>(np);
-    flood_stage_workspace(&b->flood, cv, np, max_seeds);
+    flood_stage_workspace(&b->flood, cv, np, max_seeds, node_cap);
 }
 
 }  // namespace isg
 
 using namespace isg;
 
-extern "C" size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds) {
-    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0) return 0;
+static size_t post_bytes(uint64_t n, uint64_t np, int64_t max_seeds, uint64_t node_cap) {
     Carver cv(nullptr, 0);
     PostBuffers b;
-    post_carve(&b, cv, (uint64_t)z * y * x, (uint64_t)(z + 2) * (y + 2) * (x + 2), max_seeds);
+    post_carve(&b, cv, n, np, max_seeds, node_cap);
     return cv.off + 512;
+}
+
+extern "C" size_t isg_post_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds) {
+    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0) return 0;
+    const uint64_t np = (uint64_t)(z + 2) * (y + 2) * (x + 2);
+    return post_bytes((uint64_t)z * y * x, np, max_seeds, np);
+}
+
+extern "C" size_t isg_post_workspace_bytes_capped(int64_t z, int64_t y, int64_t x, int64_t max_seeds,
+                                                  int64_t max_flood_nodes) {
+    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0 || max_flood_nodes <= 0) return 0;
+    const uint64_t np = (uint64_t)(z + 2) * (y + 2) * (x + 2);
+    return post_bytes((uint64_t)z * y * x, np, max_seeds, (uint64_t)max_flood_nodes);
+}
+
+// the largest compact-arena capacity (voxels of multi-seed components) that fits `bytes`
+static uint64_t post_node_cap_for(uint64_t n, uint64_t np, int64_t max_seeds, size_t bytes) {
+    if (post_bytes(n, np, max_seeds, np) <= bytes) return np;
+    const size_t lo_b = post_bytes(n, np, max_seeds, 1);
+    if (lo_b > bytes) return 0;
+    uint64_t lo = 1, hi = np;                  // post_bytes is monotone in the cap
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (post_bytes(n, np, max_seeds, mid) <= bytes) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, int64_t y, int64_t x,
@@ -378,10 +403,17 @@ extern "C" int isg_segment_features(const float *feats, int n_chan, int64_t z, i
     ISG_REQUIRE(prm->aff_ch[1] - c0 == prm->aff_ch[2] - prm->aff_ch[1], ISG_ERR_ARG,
                 "affinity channels must be equally spaced");
     cudaStream_t st = (cudaStream_t)stream;
+    // the compact arenas of the ordered flood take what the workspace offers beyond the fixed part:
+    // the full isg_post_workspace_bytes covers every voxel, a smaller block (sparse masks, big slabs)
+    // covers fewer and fails loudly when the multi-seed components do not fit
+    const uint64_t node_cap = post_node_cap_for(n, np, max_seeds, workspace ? workspace_bytes : 0);
+    ISG_REQUIRE(workspace && node_cap > 0, ISG_ERR_WORKSPACE,
+                "isg_segment_features: workspace too small (%zu < %zu)", workspace_bytes,
+                post_bytes(n, np, max_seeds, 1));
     Carver cv(workspace, workspace_bytes);
     PostBuffers b;
-    post_carve(&b, cv, n, np, max_seeds);
-    ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE,
+    post_carve(&b, cv, n, np, max_seeds, node_cap);
+    ISG_REQUIRE(cv.ok, ISG_ERR_WORKSPACE,
                 "isg_segment_features: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
     const uint32_t Z = (uint32_t)z, Y = (uint32_t)y, X = (uint32_t)x;
     const int sms = num_sms();

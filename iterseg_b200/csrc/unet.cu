@@ -42,6 +42,7 @@ static inline bool is_tc(int i) { return i != 0 && i != 17; }
 struct PackLayout {
     size_t w[18];          // conv weights (fp16 tap-major for tensor-core layers, fp32 otherwise)
     size_t gamma[18], beta[18];
+    size_t inv_s[18], eps[18];   // per output channel: 1 / (power-of-two prescale of the filter), BN_EPS / s^2
     size_t up_w[4], up_b[4];
     size_t total;
 };
@@ -58,6 +59,8 @@ static PackLayout pack_layout() {
         else L.w[i] = take((size_t)27 * CONVS[i].cin * CONVS[i].cout * sizeof(float));
         L.gamma[i] = take(CONVS[i].cout * sizeof(float));
         L.beta[i] = take(CONVS[i].cout * sizeof(float));
+        L.inv_s[i] = take(CONVS[i].cout * sizeof(float));
+        L.eps[i] = take(CONVS[i].cout * sizeof(float));
     }
     for (int u = 0; u < 4; ++u) {
         L.up_w[u] = take((size_t)UP_C[u] * UP_KZ[u] * 4 * sizeof(float));
@@ -155,11 +158,19 @@ struct TcLayer {
 
 struct isg_unet_plan {
     int N, Z, Y, X;
+    int cz, cy, cx;
     int D[5], H[5], W[5];
     const unsigned char *packed;
     isg::PackLayout L;
     // device buffers
     int *starts, *crop_lo, *crop_hi;
+    // chunk tables: host copy in pinned memory, uploaded by the next forward pass with
+    // cudaMemcpyAsync on ITS stream (ordered against that stream's earlier kernels)
+    unsigned int *overflow_host;  // pinned: g_unet_overflow as of the last completed forward pass
+    int *tabs_host;               // pinned, 9 * N ints: starts | crop_lo | crop_hi
+    int tabs_dirty;
+    cudaEvent_t tabs_ev;          // recorded after an upload: the pinned copy may be rewritten once it is done
+    int tabs_ev_pending;
     __half *raw[5], *act[5], *skip[4], *pooled[5], *up[4];
     float *raw8, *raw9;
     unsigned long long *stats[18];
@@ -522,10 +533,24 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         return launch_tc(p->tc[i], st);
     };
     ProfScope whole(p, 1, st);
+    if (p->tabs_dirty) {
+        if (p->tabs_dirty < 0) {
+            set_error("isg_unet_forward_chunks: no chunk tables set (isg_unet_plan_set_chunks)");
+            return ISG_ERR_ARG;
+        }
+        const size_t nb = sizeof(int) * 3 * (size_t)N;
+        ISG_CUDA(cudaMemcpyAsync(p->starts, p->tabs_host, nb, cudaMemcpyHostToDevice, st));
+        ISG_CUDA(cudaMemcpyAsync(p->crop_lo, p->tabs_host + 3 * N, nb, cudaMemcpyHostToDevice, st));
+        ISG_CUDA(cudaMemcpyAsync(p->crop_hi, p->tabs_host + 6 * N, nb, cudaMemcpyHostToDevice, st));
+        ISG_CUDA(cudaEventRecord(p->tabs_ev, st));
+        p->tabs_ev_pending = 1;
+        p->tabs_dirty = 0;
+    }
     const unsigned char *pk = p->packed;
     const PackLayout &L = p->L;
     auto G = [&](int i) { return reinterpret_cast<const float *>(pk + L.gamma[i]); };
     auto B = [&](int i) { return reinterpret_cast<const float *>(pk + L.beta[i]); };
+    auto E = [&](int i) { return reinterpret_cast<const float *>(pk + L.eps[i]); };
     auto vox = [&](int l) { return (size_t)p->D[l] * p->H[l] * p->W[l]; };
     ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
     // ---- c0.conv0 (1 -> 32, im2col on tensor cores, straight from the frame) ----
@@ -549,7 +574,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             if (stop == i0) return ISG_OK;
         }
         bn_relu_kernel<<<egrid(vox(l) * CH[l] / 8, N), 256, 0, st>>>(p->raw[l], p->act[l], p->stats[i0],
-                                                                     G(i0), B(i0), CH[l], vox(l));
+                                                                     G(i0), B(i0), E(i0), CH[l], vox(l));
         ISG_LAUNCHED();
         int rc = run_tc(i1);
         if (rc) return rc;
@@ -558,11 +583,11 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             const size_t work = vox(l + 1) * CH[l] / 8;
             if (l == 3)
                 bn_relu_pool_kernel<2><<<egrid(work, N), 256, 0, st>>>(
-                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), CH[l], p->D[l],
+                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), E(i1), CH[l], p->D[l],
                     p->H[l], p->W[l], p->D[l + 1], p->H[l + 1], p->W[l + 1]);
             else
                 bn_relu_pool_kernel<1><<<egrid(work, N), 256, 0, st>>>(
-                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), CH[l], p->D[l],
+                    p->raw[l], p->skip[l], p->pooled[l + 1], p->stats[i1], G(i1), B(i1), E(i1), CH[l], p->D[l],
                     p->H[l], p->W[l], p->D[l + 1], p->H[l + 1], p->W[l + 1]);
             ISG_LAUNCHED();
         }
@@ -578,11 +603,11 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         const int off = u == 3 ? 1 : 0;
         if (u == 0)
             bn_relu_up_kernel<2><<<egrid(work, N), 256, (size_t)(3 + 8) * C * sizeof(float), st>>>(
-                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
+                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), E(src_conv), uw, ub, C, p->D[lc],
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
         else
             bn_relu_up_kernel<1><<<egrid(work, N), 256, (size_t)(3 + 4) * C * sizeof(float), st>>>(
-                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), uw, ub, C, p->D[lc],
+                p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), E(src_conv), uw, ub, C, p->D[lc],
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
         ISG_LAUNCHED();
         const int i0 = 10 + 2 * u, i1 = i0 + 1;
@@ -592,7 +617,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         if (u < 3) {
             const int Cm = CONVS[i0].cout;
             bn_relu_kernel<<<egrid(vox(lf) * Cm / 8, N), 256, 0, st>>>(p->raw[lf], p->act[lf], p->stats[i0],
-                                                                       G(i0), B(i0), Cm, vox(lf));
+                                                                       G(i0), B(i0), E(i0), Cm, vox(lf));
             ISG_LAUNCHED();
             rc = run_tc(i1);
             if (rc) return rc;
@@ -608,7 +633,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         z.tiles_h = (z.H + ZR_HT - 1) / ZR_HT;
         z.n_cols = z.N * z.tiles_h * z.tiles_w;
         z.out = p->raw9; z.stats = p->stats[17]; z.sched = p->sched[17];
-        a.src = p->raw8; a.stats_in = p->stats[16]; a.gamma_in = G(16); a.beta_in = B(16);
+        a.src = p->raw8; a.stats_in = p->stats[16]; a.gamma_in = G(16); a.beta_in = B(16); a.eps_in = E(16);
         a.wgt = reinterpret_cast<const float *>(pk + L.w[17]);
         ISG_CUDA(cudaFuncSetAttribute(conv_out_zring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)zout_smem_bytes()));
@@ -618,7 +643,9 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         ISG_LAUNCHED();
     }
     if (feats == nullptr) return ISG_OK;
-    place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), p->starts,
+    ISG_CUDA(cudaMemcpyFromSymbolAsync(p->overflow_host, g_unet_overflow, sizeof(unsigned int), 0,
+                                       cudaMemcpyDeviceToHost, st));
+    place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), E(17), p->starts,
                                                    p->crop_lo, p->crop_hi, feats, p->Z, p->Y, p->X,
                                                    p->D[0], p->H[0], p->W[0]);
     ISG_LAUNCHED();
@@ -645,14 +672,19 @@ extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, 
         const float *gam = (const float *)tensors[14 * mi + 4 + 5 * ci];
         const float *bet = (const float *)tensors[14 * mi + 5 + 5 * ci];
         ISG_REQUIRE(w && gam && bet, ISG_ERR_ARG, "isg_unet_weights_pack: missing tensor for %s", CONVS[i].name);
+        float *inv_s = (float *)(pk + L.inv_s[i]);
+        // ISG_NO_WEIGHT_PRESCALE=1 (diagnosis / the overflow test only) packs the filters as they are
+        conv_prescale_kernel<<<CONVS[i].cout, 256, 0, st>>>(w, CONVS[i].cin, inv_s, (float *)(pk + L.eps[i]),
+                                                            getenv("ISG_NO_WEIGHT_PRESCALE") == nullptr ? 1 : 0);
+        ISG_LAUNCHED();
         if ((i == 1 || i == 15) && getenv("ISG_NO_ZRING32") == nullptr)
-            pack_conv_w_zring32_kernel<<<64, 256, 0, st>>>(w, (__half *)(pk + L.w[i]));
+            pack_conv_w_zring32_kernel<<<64, 256, 0, st>>>(w, inv_s, (__half *)(pk + L.w[i]));
         else if (i == 16)
-            pack_conv_w_zring_kernel<<<64, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
+            pack_conv_w_zring_kernel<<<64, 256, 0, st>>>(w, inv_s, (__half *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
         else if (is_tc(i))
-            pack_conv_w_kernel<<<256, 256, 0, st>>>(w, (__half *)(pk + L.w[i]), CONVS[i].cout, cout_pad(i), CONVS[i].cin);
+            pack_conv_w_kernel<<<256, 256, 0, st>>>(w, inv_s, (__half *)(pk + L.w[i]), CONVS[i].cout, cout_pad(i), CONVS[i].cin);
         else
-            pack_conv_w_f32_kernel<<<16, 256, 0, st>>>(w, (float *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
+            pack_conv_w_f32_kernel<<<16, 256, 0, st>>>(w, inv_s, (float *)(pk + L.w[i]), CONVS[i].cout, CONVS[i].cin);
         ISG_LAUNCHED();
         copy_f32_kernel<<<1, 256, 0, st>>>(gam, (float *)(pk + L.gamma[i]), CONVS[i].cout);
         ISG_LAUNCHED();
@@ -686,7 +718,8 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
                                                const int32_t *starts_host, const int32_t *crop_lo_host,
                                                const int32_t *crop_hi_host, void *workspace,
                                                size_t workspace_bytes) {
-    if (!packed_weights || !starts_host || !crop_lo_host || !crop_hi_host || !workspace || n_chunks <= 0) {
+    if (!packed_weights || !workspace || n_chunks <= 0 ||
+        ((starts_host || crop_lo_host || crop_hi_host) && !(starts_host && crop_lo_host && crop_hi_host))) {
         set_error("isg_unet_plan_create: bad argument");
         return nullptr;
     }
@@ -713,14 +746,6 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
         delete p;
         return nullptr;
     }
-    for (int n = 0; n < n_chunks; ++n) {
-        const int32_t *s = starts_host + 3 * n;
-        if (s[0] < 0 || s[1] < 0 || s[2] < 0 || s[0] + cz > z || s[1] + cy > y || s[2] + cx > x) {
-            set_error("chunk %d starts outside the frame", n);
-            delete p;
-            return nullptr;
-        }
-    }
     Carver cv(workspace, workspace_bytes);
     plan_carve(p, cv);
     if (!cv.ok) {
@@ -728,9 +753,26 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
         delete p;
         return nullptr;
     }
-    cudaMemcpy(p->starts, starts_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
-    cudaMemcpy(p->crop_lo, crop_lo_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
-    cudaMemcpy(p->crop_hi, crop_hi_host, sizeof(int) * 3 * n_chunks, cudaMemcpyHostToDevice);
+    p->cz = cz; p->cy = cy; p->cx = cx;
+    p->tabs_host = nullptr;
+    p->overflow_host = nullptr;
+    p->tabs_ev = nullptr;
+    p->tabs_ev_pending = 0;
+    p->tabs_dirty = -1;                                   // nothing set yet
+    if (cudaHostAlloc((void **)&p->overflow_host, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess)
+        *p->overflow_host = 0;
+    if (!p->overflow_host ||
+        cudaHostAlloc((void **)&p->tabs_host, sizeof(int) * 9 * (size_t)n_chunks, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->tabs_ev, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("isg_unet_plan_create: pinned staging for the chunk tables: %s",
+                  cudaGetErrorString(cudaGetLastError()));
+        isg_unet_plan_destroy(p);
+        return nullptr;
+    }
+    if (starts_host && isg_unet_plan_set_chunks(p, starts_host, crop_lo_host, crop_hi_host) != ISG_OK) {
+        isg_unet_plan_destroy(p);
+        return nullptr;
+    }
     bool ok = true;
     // encoder
     ok = ok && setup_tc_layer(p, 1, p->act[0], 32, nullptr, 0, p->raw[0], 0);
@@ -751,7 +793,7 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
     ok = ok && setup_tc_layer(p, 15, p->act[1], 32, nullptr, 0, p->raw[1], 0);
     ok = ok && setup_tc_layer(p, 16, p->up[0], 32, p->skip[0], 32, p->raw8, 1);
     if (!ok) {
-        delete p;
+        isg_unet_plan_destroy(p);
         return nullptr;
     }
     double macs = 0, tc_macs = 0;
@@ -773,7 +815,57 @@ extern "C" isg_unet_plan *isg_unet_plan_create(const void *packed_weights, int n
 extern "C" void isg_unet_plan_destroy(isg_unet_plan *plan) {
     if (!plan) return;
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    if (plan->tabs_ev) {
+        if (plan->tabs_ev_pending) cudaEventSynchronize(plan->tabs_ev);   // an upload may still read tabs_host
+        cudaEventDestroy(plan->tabs_ev);
+    }
+    if (plan->tabs_host) cudaFreeHost(plan->tabs_host);
+    if (plan->overflow_host) cudaFreeHost(plan->overflow_host);
     delete plan;
+}
+
+extern "C" int isg_unet_plan_overflowed(const isg_unet_plan *plan) {
+    return plan && plan->overflow_host ? (int)*reinterpret_cast<volatile unsigned int *>(plan->overflow_host) : 0;
+}
+
+extern "C" int isg_unet_plan_clear_overflow(isg_unet_plan *plan, void *stream) {
+    ISG_REQUIRE(plan, ISG_ERR_ARG, "isg_unet_plan_clear_overflow: null plan");
+    const unsigned int zero = 0;
+    *plan->overflow_host = 0;
+    ISG_CUDA(cudaMemcpyToSymbolAsync(g_unet_overflow, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice,
+                                     (cudaStream_t)stream));
+    return ISG_OK;
+}
+
+extern "C" int isg_unet_plan_set_chunks(isg_unet_plan *plan, const int32_t *starts_host,
+                                        const int32_t *crop_lo_host, const int32_t *crop_hi_host) {
+    ISG_REQUIRE(plan && starts_host && crop_lo_host && crop_hi_host, ISG_ERR_ARG,
+                "isg_unet_plan_set_chunks: null pointer");
+    const int N = plan->N;
+    for (int n = 0; n < N; ++n) {
+        const int32_t *s = starts_host + 3 * n, *lo = crop_lo_host + 3 * n, *hi = crop_hi_host + 3 * n;
+        const int64_t ext[3] = {plan->Z, plan->Y, plan->X};
+        const int chk[3] = {plan->cz, plan->cy, plan->cx};
+        for (int a = 0; a < 3; ++a) {
+            ISG_REQUIRE(s[a] >= 0 && s[a] + chk[a] <= ext[a], ISG_ERR_ARG, "chunk %d starts outside the frame", n);
+            ISG_REQUIRE(lo[a] >= 0 && lo[a] <= hi[a] && hi[a] <= chk[a], ISG_ERR_ARG,
+                        "chunk %d: crop [%d,%d) outside the chunk extent %d", n, lo[a], hi[a], chk[a]);
+        }
+    }
+    if (plan->tabs_ev_pending) {                           // the previous upload still reads the pinned copy
+        ISG_CUDA(cudaEventSynchronize(plan->tabs_ev));
+        plan->tabs_ev_pending = 0;
+    }
+    const size_t nb = sizeof(int) * 3 * (size_t)N;
+    if (plan->tabs_dirty == 0 && memcmp(plan->tabs_host, starts_host, nb) == 0 &&
+        memcmp(plan->tabs_host + 3 * N, crop_lo_host, nb) == 0 &&
+        memcmp(plan->tabs_host + 6 * N, crop_hi_host, nb) == 0)
+        return ISG_OK;                                     // the device already holds these tables
+    memcpy(plan->tabs_host, starts_host, nb);
+    memcpy(plan->tabs_host + 3 * N, crop_lo_host, nb);
+    memcpy(plan->tabs_host + 6 * N, crop_hi_host, nb);
+    plan->tabs_dirty = 1;
+    return ISG_OK;
 }
 
 extern "C" int isg_unet_plan_profile(isg_unet_plan *plan, int enable) {
@@ -805,6 +897,9 @@ extern "C" double isg_unet_plan_flops(const isg_unet_plan *plan) { return plan ?
 
 extern "C" int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream) {
     ISG_REQUIRE(plan && frame && feats, ISG_ERR_ARG, "isg_unet_forward_chunks: null pointer");
+    ISG_REQUIRE(!isg_unet_plan_overflowed(plan), ISG_ERR_OVERFLOW,
+                "isg_unet_forward_chunks: an earlier forward pass of this plan overflowed the fp16 range of the "
+                "pre-BatchNorm activations (its feature volume is invalid); isg_unet_plan_clear_overflow re-arms");
     return forward(plan, frame, feats, 17, (cudaStream_t)stream);
 }
 
@@ -828,7 +923,8 @@ extern "C" int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame
     if (idx == 16) { src = plan->raw8 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
     else if (idx == 17) { src = plan->raw9 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
     else src = plan->raw[l] + (size_t)chunk * vox * cstride;
-    debug_to_ncdhw_kernel<<<num_sms() * 4, 256, 0, st>>>(src, is_f32, cstride, C, vox, out);
+    debug_to_ncdhw_kernel<<<num_sms() * 4, 256, 0, st>>>(
+        src, is_f32, cstride, C, vox, reinterpret_cast<const float *>(plan->packed + plan->L.inv_s[idx]), out);
     ISG_LAUNCHED();
     return ISG_OK;
 }

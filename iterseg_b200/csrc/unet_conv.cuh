@@ -77,6 +77,17 @@ struct ConvGeom {
                                  // first one of a CTA are handed out dynamically, see "scheduler" below
 };
 
+// fp16 range guard.  The pre-BatchNorm activations are stored as fp16 (ceiling 65504); the filters
+// are prescaled at pack time so that they are O(1), but nothing can rule out pathological
+// weights.  Every kernel that reduces BatchNorm sums checks the per-warp sum of 32 squares it has
+// anyway: >= 1e9 (some |x| >= 5590), inf or NaN raises this sticky device flag, which the host
+// reads back after every forward pass and turns into an error (isg_unet_plan_overflowed) --
+// never a silent inf / NaN in the feature volume.
+__device__ unsigned int g_unet_overflow;
+__device__ __forceinline__ void stat_guard(float q2) {
+    if (!(q2 < 1.0e9f)) g_unet_overflow = 1u;
+}
+
 static constexpr int CONV_THREADS = 256;
 static constexpr float STAT_SCALE = 16777216.0f;      // 2^24
 static constexpr int CONV_SLACK = 4096;      // garbage rows the last taps of invalid rows touch
@@ -469,6 +480,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             q2 = fmaf(x, x, q2);
                         }
                         __syncwarp();
+                        stat_guard(q2);
                         csum[i] += __float2ll_rn(s * STAT_SCALE);
                         csq[i] += __float2ll_rn(q2 * STAT_SCALE);
                     }
@@ -509,6 +521,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
                 __syncwarp();
+                stat_guard(q2);
                 csum[0] += __float2ll_rn(s * STAT_SCALE);
                 csq[0] += __float2ll_rn(q2 * STAT_SCALE);
             }

@@ -18,12 +18,15 @@ static constexpr float BN_EPS = 1e-5f;
 
 // BatchNorm3d in training mode: batch statistics (biased variance) of ONE chunk.
 // stats_c = (sum, sum of squares) in 2^-24 fixed point (see STAT_SCALE in unet_conv.cuh).
-__device__ __forceinline__ void bn_coeffs(const unsigned long long *stats_c, float gamma, float beta,
+// eps: BN_EPS / s^2 where s is the power of two the layer's weights of this output channel were
+// divided by when they were packed (isg_unet_weights_pack): the stored convolution output is
+// raw / s, and gamma * (raw - mean) / sqrt(var + eps) == gamma * (raw/s - mean/s) / sqrt(var/s^2 + eps/s^2).
+__device__ __forceinline__ void bn_coeffs(const unsigned long long *stats_c, float gamma, float beta, float eps,
                                           float inv_count, float &scale, float &shift) {
     const double k = (double)inv_count / 16777216.0;
     const double mean = (double)(long long)stats_c[0] * k;
     const double var = fmax((double)(long long)stats_c[1] * k - mean * mean, 0.0);
-    const float inv = 1.0f / sqrtf((float)var + BN_EPS);
+    const float inv = 1.0f / sqrtf((float)var + eps);
     scale = gamma * inv;
     shift = beta - (float)mean * scale;
 }
@@ -55,11 +58,11 @@ __device__ __forceinline__ int bn_slot(int c, int groups) {
     return ((c >> 2) & 1) * (groups * 4) + (c >> 3) * 4 + (c & 3);
 }
 __device__ __forceinline__ void bn_table4(float4 *tab, const unsigned long long *stats, const float *gamma,
-                                          const float *beta, int C, int n, float inv_count) {
+                                          const float *beta, const float *eps, int C, int n, float inv_count) {
     float *t = reinterpret_cast<float *>(tab);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sc, sh;
-        bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], inv_count, sc, sh);
+        bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], eps[c], inv_count, sc, sh);
         t[bn_slot(c, C / 8)] = sc;
         t[C + bn_slot(c, C / 8)] = sh;
     }
@@ -81,10 +84,11 @@ __device__ __forceinline__ void bn_relu8(const float4 *tab, int groups, int g, f
 // raw -> relu(bn(raw)), same shape.  grid = (blocks, N)
 __global__ void __launch_bounds__(256)
 bn_relu_kernel(const __half *__restrict__ raw, __half *__restrict__ act, const unsigned long long *__restrict__ stats,
-               const float *__restrict__ gamma, const float *__restrict__ beta, int C, size_t vox) {
+               const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ eps,
+               int C, size_t vox) {
     __shared__ float4 tab[128];                          // C <= 256
     const int n = blockIdx.y;
-    bn_table4(tab, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    bn_table4(tab, stats, gamma, beta, eps, C, n, 1.0f / (float)vox);
     const int groups = C / 8;
     const size_t total = vox * groups;
     const __half *src = raw + (size_t)n * vox * C;
@@ -105,12 +109,13 @@ template <int PZ>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(const __half *__restrict__ raw, __half *__restrict__ skip,
                     __half *__restrict__ pooled, const unsigned long long *__restrict__ stats,
-                    const float *__restrict__ gamma, const float *__restrict__ beta, int C, int D,
+                    const float *__restrict__ gamma, const float *__restrict__ beta,
+                    const float *__restrict__ eps, int C, int D,
                     int H, int W, int Dc, int Hc, int Wc) {
     __shared__ float4 tab[128];                          // C <= 256
     const int n = blockIdx.y;
     const size_t vox = (size_t)D * H * W;
-    bn_table4(tab, stats, gamma, beta, C, n, 1.0f / (float)vox);
+    bn_table4(tab, stats, gamma, beta, eps, C, n, 1.0f / (float)vox);
     const int groups = C / 8;
     const size_t total = (size_t)Dc * Hc * Wc * groups;
     const __half *src = raw + (size_t)n * vox * C;
@@ -174,7 +179,8 @@ template <int KZ>
 __global__ void __launch_bounds__(256)
 bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
                   const unsigned long long *__restrict__ stats, const float *__restrict__ gamma,
-                  const float *__restrict__ beta, const float *__restrict__ wgt,
+                  const float *__restrict__ beta, const float *__restrict__ eps,
+                  const float *__restrict__ wgt,
                   const float *__restrict__ bias, int C, int Dc, int Hc, int Wc, int Df, int Hf,
                   int Wf, int off) {
     constexpr int TAPS = KZ * 4;
@@ -188,7 +194,7 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
         auto slot = [&](int c) { return ((c >> 2) & 1) * (groups * 4) + (c >> 3) * 4 + (c & 3); };
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             float sc, sh;
-            bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], 1.0f / (float)vox, sc, sh);
+            bn_coeffs(stats + ((size_t)n * C + c) * 2, gamma[c], beta[c], eps[c], 1.0f / (float)vox, sc, sh);
             tab[0 * C + slot(c)] = sc;
             tab[1 * C + slot(c)] = sh;
             tab[2 * C + slot(c)] = bias[c];
@@ -244,7 +250,7 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
 // (5, Z, Y, X) feature volume (predict.py:89-95): each voxel is written by exactly one chunk.
 __global__ void __launch_bounds__(256)
 place_kernel(const float *__restrict__ raw9, const unsigned long long *__restrict__ stats9,
-             const float *__restrict__ gamma, const float *__restrict__ beta,
+             const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ eps,
              const int *__restrict__ starts, const int *__restrict__ crop_lo,
              const int *__restrict__ crop_hi, float *__restrict__ feats, int Z, int Y, int X, int D,
              int H, int W) {
@@ -253,7 +259,7 @@ place_kernel(const float *__restrict__ raw9, const unsigned long long *__restric
     const size_t vox = (size_t)D * H * W;
     if (threadIdx.x < 5)
         bn_coeffs(stats9 + ((size_t)n * 5 + threadIdx.x) * 2, gamma[threadIdx.x], beta[threadIdx.x],
-                  1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
+                  eps[threadIdx.x], 1.0f / (float)vox, sc[threadIdx.x], sh[threadIdx.x]);
     __syncthreads();
     const int lz = crop_lo[n * 3], ly = crop_lo[n * 3 + 1], lx = crop_lo[n * 3 + 2];
     const int cd = crop_hi[n * 3] - lz, ch = crop_hi[n * 3 + 1] - ly, cw = crop_hi[n * 3 + 2] - lx;
@@ -281,7 +287,42 @@ place_kernel(const float *__restrict__ raw9, const unsigned long long *__restric
 
 // ---- weight packing -------------------------------------------------------------
 // nn.Conv3d weight (Cout, Cin, 3,3,3) fp32 -> [tap][cout_pad][cin] fp16 (rows >= Cout zero)
-__global__ void pack_conv_w_kernel(const float *__restrict__ src, __half *__restrict__ dst, int cout,
+// Per output channel: s = 2^ceil(log2(||w_co||_2)) (1 for an all-zero filter), inv_s = 1 / s,
+// eps = BN_EPS / s^2.  Every convolution is followed by a train-mode BatchNorm, which makes the
+// network's output invariant to the scale of a filter (up to eps, handled in bn_coeffs); packing
+// w / s keeps the fp16 weights and the fp16 pre-BatchNorm activations O(1) whatever scale a
+// training run left the filters at -- fp16 has a 65504 ceiling that the reference's fp32 (and
+// bf16) do not have.  Powers of two: the division is exact.
+__global__ void __launch_bounds__(256)
+conv_prescale_kernel(const float *__restrict__ src, int cin, float *__restrict__ inv_s, float *__restrict__ eps,
+                     int enable) {
+    __shared__ double part[256];
+    const int co = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < cin * 27; i += blockDim.x) {
+        const double v = (double)src[(size_t)co * cin * 27 + i];
+        acc += v * v;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) part[threadIdx.x] += part[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int e = 0;
+        const double nrm = sqrt(part[0]);
+        if (enable && nrm > 0.0 && isfinite(nrm)) {
+            e = (int)ceil(log2(nrm));
+            e = e < -60 ? -60 : (e > 60 ? 60 : e);
+        }
+        inv_s[co] = (float)ldexp(1.0, -e);
+        eps[co] = (float)ldexp((double)BN_EPS, -2 * e);
+    }
+}
+
+__global__ void pack_conv_w_kernel(const float *__restrict__ src, const float *__restrict__ inv_s,
+                                   __half *__restrict__ dst, int cout,
                                    int cout_pad, int cin) {
     const size_t total = (size_t)27 * cout_pad * cin;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -291,20 +332,20 @@ __global__ void pack_conv_w_kernel(const float *__restrict__ src, __half *__rest
         const int co = (int)(t % cout_pad);
         const int tap = (int)(t / cout_pad);
         float v = 0.0f;
-        if (co < cout) v = src[((size_t)co * cin + ci) * 27 + tap];
+        if (co < cout) v = src[((size_t)co * cin + ci) * 27 + tap] * inv_s[co];
         dst[i] = __float2half_rn(v);
     }
 }
 // (Cout, Cin, 27) fp32 -> [tap][cin][cout] fp32 (CUDA-core layers)
-__global__ void pack_conv_w_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int cout,
-                                       int cin) {
+__global__ void pack_conv_w_f32_kernel(const float *__restrict__ src, const float *__restrict__ inv_s,
+                                       float *__restrict__ dst, int cout, int cin) {
     const int total = 27 * cin * cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int co = i % cout;
         const int t = i / cout;
         const int ci = t % cin;
         const int tap = t / cin;
-        dst[i] = src[((size_t)co * cin + ci) * 27 + tap];
+        dst[i] = src[((size_t)co * cin + ci) * 27 + tap] * inv_s[co];
     }
 }
 __global__ void copy_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int n) {
@@ -313,14 +354,15 @@ __global__ void copy_f32_kernel(const float *__restrict__ src, float *__restrict
 
 // fp16 channels-last [vox][C] of one chunk -> fp32 [C][vox] (debug / parity only)
 __global__ void debug_to_ncdhw_kernel(const void *__restrict__ src, int is_f32, int cstride, int C,
-                                      size_t vox, float *__restrict__ dst) {
+                                      size_t vox, const float *__restrict__ inv_s, float *__restrict__ dst) {
     const size_t total = vox * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
         const size_t v = i % vox;
         const int c = (int)(i / vox);
-        dst[i] = is_f32 ? reinterpret_cast<const float *>(src)[v * cstride + c]
-                        : __half2float(reinterpret_cast<const __half *>(src)[v * cstride + c]);
+        const float x = is_f32 ? reinterpret_cast<const float *>(src)[v * cstride + c]
+                               : __half2float(reinterpret_cast<const __half *>(src)[v * cstride + c]);
+        dst[i] = x / inv_s[c];                       // undo the filter's power-of-two prescale (exact)
     }
 }
 

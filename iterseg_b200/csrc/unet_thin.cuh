@@ -208,6 +208,7 @@ conv_in_tc_kernel(const ThinArgs a) {
             q2 = fmaf(x, x, q2);
         }
         __syncwarp();
+        stat_guard(q2);
         csum += __float2ll_rn(s * 16777216.0f);
         csq += __float2ll_rn(q2 * 16777216.0f);
     }

@@ -176,6 +176,7 @@ __device__ __forceinline__ void zring_epilogue(const ZringGeom &g, uint32_t tmem
                 q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, 8);
                 s += __shfl_xor_sync(0xFFFFFFFFu, s, 16);
                 q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, 16);
+                stat_guard(q2);
                 csum += __float2ll_rn(s * 16777216.0f);            // lanes >= 8 hold copies; only lanes < 5 flush
                 csq += __float2ll_rn(q2 * 16777216.0f);
             }
@@ -360,7 +361,7 @@ struct ZoutArgs {
     ZringGeom g;                          // out = raw9 fp32 [N][vox][8], stats = stats9 [N][5][2]
     const float *src;                     // raw8 fp32 [N][vox][8]
     const unsigned long long *stats_in;   // [N][16][2]
-    const float *gamma_in, *beta_in;
+    const float *gamma_in, *beta_in, *eps_in;
     const float *wgt;                     // [27][5 in][5 out] fp32
 };
 
@@ -463,7 +464,7 @@ conv_out_zring_kernel(const ZoutArgs a) {
                 cur_n = n;
 #pragma unroll
                 for (int c = 0; c < 5; ++c)
-                    bn_coeffs(a.stats_in + ((size_t)n * 16 + c) * 2, a.gamma_in[c], a.beta_in[c],
+                    bn_coeffs(a.stats_in + ((size_t)n * 16 + c) * 2, a.gamma_in[c], a.beta_in[c], a.eps_in[c],
                               1.0f / (float)vox_chunk, sc[c], sh[c]);
             }
             // in-plane positions of the two rows (the same for every plane of the column)
@@ -559,7 +560,8 @@ conv_out_zring_kernel(const ZoutArgs a) {
 
 // nn.Conv3d weight (5, 64, 3,3,3) fp32 -> [dy][(dz*3 + dx) * 8 + co][cin] fp16, 80 rows per dy
 // (co >= 5 and rows >= 72 zero)
-__global__ void pack_conv_w_zring_kernel(const float *__restrict__ src, __half *__restrict__ dst, int cout, int cin) {
+__global__ void pack_conv_w_zring_kernel(const float *__restrict__ src, const float *__restrict__ inv_s,
+                                         __half *__restrict__ dst, int cout, int cin) {
     const int total = 3 * ZR_N * cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % cin;
@@ -569,7 +571,7 @@ __global__ void pack_conv_w_zring_kernel(const float *__restrict__ src, __half *
         float v = 0.0f;
         if (t9 < 9 && co < cout) {
             const int dz = t9 / 3, dx = t9 % 3;
-            v = src[((size_t)co * cin + ci) * 27 + dz * 9 + dy * 3 + dx];
+            v = src[((size_t)co * cin + ci) * 27 + dz * 9 + dy * 3 + dx] * inv_s[co];
         }
         dst[i] = __float2half_rn(v);
     }

@@ -246,6 +246,7 @@ conv3d_zring32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     q2 = fmaf(x, x, q2);
                 }
                 __syncwarp();
+                stat_guard(q2);
                 csum += __float2ll_rn(s * 16777216.0f);
                 csq += __float2ll_rn(q2 * 16777216.0f);
                 tc_fence_before();
@@ -265,14 +266,15 @@ conv3d_zring32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // nn.Conv3d weight (32, 32, 3,3,3) fp32 -> [dy*3 + dx][dz*32 + co][cin] fp16
-__global__ void pack_conv_w_zring32_kernel(const float *__restrict__ src, __half *__restrict__ dst) {
+__global__ void pack_conv_w_zring32_kernel(const float *__restrict__ src, const float *__restrict__ inv_s,
+                                           __half *__restrict__ dst) {
     const int total = 9 * Z32_N * 32;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i & 31;
         const int row = (i >> 5) % Z32_N;
         const int t = i / (32 * Z32_N);                  // dy*3 + dx
         const int dz = row >> 5, co = row & 31;
-        dst[i] = __float2half_rn(src[((size_t)co * 32 + ci) * 27 + dz * 9 + t]);
+        dst[i] = __float2half_rn(src[((size_t)co * 32 + ci) * 27 + dz * 9 + t] * inv_s[co]);
     }
 }
 

@@ -17,8 +17,47 @@ from . import _lib
 
 
 def shard_frames(n_frames, rank, world_size):
-    """Frames t = rank (mod world_size): consecutive frames land on different GPUs."""
+    """Frames t = rank (mod world_size): consecutive frames land on different GPUs, every rank
+    walks the series in time order, and step s of all ranks covers the frames s*R .. s*R+R-1
+    (what makes a running global label offset one all-gather per step)."""
     return list(range(int(rank), int(n_frames), int(world_size)))
+
+
+def world(group=None):
+    """(rank, world_size) of the initialised torch.distributed job, else (0, 1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class LabelOffsets:
+    """Running global label offset of a frame-sharded series, kept on the device.
+
+    Step s: every rank contributes the label count of its frame s*R + rank (0 when it has
+    none); one all-gather of R int64 (NCCL over NVLink; gloo on CPU tensors) gives the exclusive
+    prefix inside the step, a device-resident total carries the earlier steps.  Nothing is
+    read back to the host: `step` returns a 1-element int64 tensor that the crop kernel
+    (isg_crop_labels) adds to the non-zero labels of this rank's frame.  All ranks must call
+    `step` the same number of times (ceil(T / R))."""
+
+    def __init__(self, rank, world_size, device, group=None):
+        self.rank, self.world, self.group = int(rank), int(world_size), group
+        self.total = torch.zeros(1, dtype=torch.int64, device=device)
+        self.gathered = torch.zeros(self.world, dtype=torch.int64, device=device)
+
+    def step(self, count):
+        """count: 1-element int64 tensor on the device (or None: no frame in this step)."""
+        c = count.reshape(1).to(torch.int64) if count is not None else torch.zeros_like(self.total)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered, c.contiguous(), group=self.group)
+            off = self.total + self.gathered[:self.rank].sum()
+            self.total = self.total + self.gathered.sum()
+        else:
+            off = self.total.clone()
+            self.total = self.total + c
+        return off
 
 
 def exclusive_offsets(counts):

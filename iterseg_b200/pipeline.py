@@ -77,3 +77,186 @@ class FramePipeline:
         stream = stream or torch.cuda.current_stream(self.dev)
         stream.wait_stream(self.s_unet)
         stream.wait_stream(self.s_post)
+
+
+class DogCore:
+    """The submit / collect interface of FramePipeline for the DoG blob segmenter
+    (segmentation.py:592-650): the whole frame is one device call, enqueued at submit time on one
+    stream; two label slots so that the copy-out of frame i overlaps frame i+1."""
+
+    def __init__(self, shape, dev, **dog_kw):
+        self.shape = tuple(int(s) for s in shape)
+        self.dev = dev
+        self.dog_kw = dog_kw
+        shape_p = tuple(s + 2 for s in self.shape)
+        with torch.cuda.device(dev):
+            self.s_unet = self.s_post = torch.cuda.Stream(dev)
+            self.slots = [{'labels': torch.zeros(shape_p, dtype=torch.int32, device=dev), 'counts': None,
+                           'ev_post': torch.cuda.Event(), 'busy': False} for _ in range(2)]
+        self.n_in = self.n_out = 0
+
+    def submit(self, frame):
+        from . import segmentation
+        k = self.n_in % 2
+        slot = self.slots[k]
+        assert not slot['busy'], 'pipeline full: collect() a frame first'
+        self.s_post.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.s_post):
+            slot['labels'].zero_()
+            _, counts = segmentation.dog_blob_segment_device(frame, slot['labels'], **self.dog_kw)
+            c8 = torch.zeros(8, dtype=torch.int64, device=self.dev)
+            c8[:4] = counts
+            slot['ev_post'].record(self.s_post)
+        frame.record_stream(self.s_post)
+        slot['counts'] = c8
+        slot['busy'] = True
+        self.n_in += 1
+        return k
+
+    def collect(self):
+        slot = self.slots[self.n_out % 2]
+        assert slot['busy'], 'nothing submitted'
+        slot['busy'] = False
+        self.last_post_event = slot['ev_post']
+        self.n_out += 1
+        return slot['labels'], slot['counts']
+
+
+class SeriesPipeline:
+    """Host frames in, host labels out, several frames in flight (the frame loop of
+    segmentation.py:873-882 without a host synchronisation on the compute streams):
+
+      loader threads   data[t] -> float32 in a pinned ring buffer (or the caller's own array when it
+                       is already pinned float32)                       [host, off the main thread]
+      s_copy           H2D of frame t+1, its min / max (isg_frame_minmax) and the 8-byte read-back
+                       that decides the reference's `min() == 0` branch -- the main thread waits
+                       for THIS event only, which never waits for a U-Net
+      s_unet           vol /= max (isg_frame_divide_by_max), chunked U-Net of frame t
+      s_post           seeds / mask / components / flood of frame t-1, crop of the padded labels
+                       (+ the device-resident global label offset) into a contiguous buffer
+      s_d2h            one contiguous D2H per frame into a pinned ring buffer (or straight into
+                       the caller's array when that is pinned)
+      writer threads   wait for the D2H event, store into `output_labels` (numpy / zarr store)
+
+    `core` is a FramePipeline (affinity U-Net watershed) or a DogCore."""
+
+    N_IN = 4        # pinned input buffers / device frame buffers
+    N_OUT = 3       # device crop buffers / pinned output buffers
+
+    def __init__(self, core, normalise=True):
+        import queue
+        self.core, self.dev, self.shape = core, core.dev, core.shape
+        self.normalise = normalise
+        self.lib = _lib.load()
+        n = 1
+        for s in self.shape:
+            n *= s
+        self.nvox = n
+        with torch.cuda.device(self.dev):
+            self.s_copy, self.s_d2h = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+            self.stage = [{'frame': torch.empty(self.shape, dtype=torch.float32, device=self.dev),
+                           'mm': torch.zeros(2, dtype=torch.float32, device=self.dev),
+                           'mm_host': torch.zeros(2, dtype=torch.float32).pin_memory(),
+                           'scratch': torch.empty(64, dtype=torch.uint8, device=self.dev),
+                           'ev_stage': torch.cuda.Event(), 'ev_consumed': torch.cuda.Event()}
+                          for _ in range(self.N_IN)]
+            self.outs = [{'crop': torch.empty(self.shape, dtype=torch.int32, device=self.dev),
+                          'host': None, 'ev_post': torch.cuda.Event(), 'ev_d2h': torch.cuda.Event()}
+                         for _ in range(self.N_OUT)]
+        self.free_in = queue.Queue()
+        for _ in range(self.N_IN):
+            self.free_in.put(torch.empty(self.shape, dtype=torch.float32).pin_memory())
+        self.free_out = queue.Queue()
+        for o in range(self.N_OUT):
+            self.free_out.put(o)
+        self.n_staged = 0
+        torch.cuda.synchronize(self.dev)
+
+    # ---- host side of the input (loader threads) -------------------------------------------
+    def load(self, src):
+        """-> ('direct', pinned float32 tensor viewing the caller's memory) or ('buf', pinned ring
+        buffer holding np.asarray(src).astype(float32))."""
+        import numpy as np
+        if isinstance(src, np.ndarray) and src.dtype == np.float32 and src.flags.c_contiguous:
+            t = torch.from_numpy(src)
+            if t.is_pinned():
+                return 'direct', t
+        buf = self.free_in.get()
+        np.copyto(buf.numpy(), np.asarray(src), casting='unsafe')
+        return 'buf', buf
+
+    # ---- main thread ---------------------------------------------------------------------------
+    def h2d(self, loaded):
+        """Enqueue the H2D copy + min / max of one loaded frame on the copy stream."""
+        kind, host = loaded
+        j = self.n_staged % self.N_IN
+        st = self.stage[j]
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.s_copy):
+            self.s_copy.wait_event(st['ev_consumed'])           # the U-Net that read this buffer last
+            st['frame'].copy_(host, non_blocking=True)
+            _lib.check(self.lib.isg_frame_minmax(st['frame'].data_ptr(), self.nvox, st['mm'].data_ptr(),
+                                                 st['scratch'].data_ptr(), st['scratch'].numel(),
+                                                 _lib.stream_ptr()), 'isg_frame_minmax')
+            st['mm_host'].copy_(st['mm'], non_blocking=True)
+            st['ev_stage'].record(self.s_copy)
+        st['host'] = (kind, host)
+        self.n_staged += 1
+        return j
+
+    def submit(self, j):
+        """Frame in staging slot j -> compute.  Returns False (nothing enqueued) when the frame
+        contains zeros: the caller takes the reference's host route (zero-slice strip)."""
+        st = self.stage[j]
+        st['ev_stage'].synchronize()                            # copy stream only
+        kind, host = st.pop('host')
+        if kind == 'buf':
+            self.free_in.put(host)
+        if self.normalise and float(st['mm_host'][0]) == 0.0:
+            return False
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            if self.normalise:
+                with torch.cuda.stream(self.core.s_unet):
+                    self.core.s_unet.wait_stream(cur)
+                    _lib.check(self.lib.isg_frame_divide_by_max(st['frame'].data_ptr(), self.nvox,
+                                                                st['mm'].data_ptr(), _lib.stream_ptr()),
+                               'isg_frame_divide_by_max')
+                with torch.cuda.stream(self.core.s_unet):       # submit() makes s_unet wait for "current"
+                    self.core.submit(st['frame'])
+            else:
+                self.core.submit(st['frame'])
+            st['ev_consumed'].record(self.core.s_unet)
+        return True
+
+    def collect(self, dst=None, offset_dev=None, on_counts=None):
+        """Post stage of the oldest submitted frame, crop, D2H.  `dst`: optional pinned int32
+        (Z,Y,X) tensor to copy into directly.  `on_counts(counts)` runs on the post stream right
+        after the post stage and may return the device int64 offset tensor for this frame.
+        Returns (o, host tensor, counts): wait for self.outs[o]['ev_d2h'], then release(o)."""
+        o = self.free_out.get()                                  # back-pressure from the writers
+        out = self.outs[o]
+        lab, counts = self.core.collect()
+        Z, Y, X = self.shape
+        with torch.cuda.device(self.dev):
+            with torch.cuda.stream(self.core.s_post):
+                if on_counts is not None:
+                    offset_dev = on_counts(counts)
+                self.core.s_post.wait_event(out['ev_d2h'])       # the previous copy out of this buffer
+                _lib.check(self.lib.isg_crop_labels(lab.data_ptr(), Z, Y, X, out['crop'].data_ptr(),
+                                                    offset_dev.data_ptr() if offset_dev is not None else None,
+                                                    _lib.stream_ptr()), 'isg_crop_labels')
+                out['ev_post'].record(self.core.s_post)
+                if offset_dev is not None:
+                    offset_dev.record_stream(self.core.s_post)
+            if dst is None:
+                if out['host'] is None:
+                    out['host'] = torch.empty(self.shape, dtype=torch.int32).pin_memory()
+                dst = out['host']
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(out['ev_post'])
+                dst.copy_(out['crop'], non_blocking=True)
+                out['ev_d2h'].record(self.s_d2h)
+        return o, dst, counts
+
+    def release(self, o):
+        self.free_out.put(o)

@@ -24,9 +24,27 @@ IGNORE_CUDA = False      # kept for interface compatibility; this implementation
 
 DEFAULT_UNET_PATH = os.path.join(os.path.dirname(__file__), 'data', '232208_161159_plateseg.pt')
 
-# chunks of one forward_chunks call (bounds the activation workspace: ~0.4 GB per
-# (10,256,256) chunk)
+# chunks of one forward_chunks call: an upper bound; `chunks_per_batch` lowers it so that the
+# activation workspace (~0.36 GB per (10,256,256) chunk) uses at most half of the free memory
 MAX_CHUNKS_PER_BATCH = 72
+
+
+def chunks_per_batch(unet, chunk_size, n_chunks):
+    """How many chunks one forward_chunks call takes: all of them up to MAX_CHUNKS_PER_BATCH,
+    fewer when the device is short of memory (the workspace the network already holds counts as
+    available).  Raises when not even one chunk fits."""
+    n = max(1, min(int(n_chunks), MAX_CHUNKS_PER_BATCH))
+    free, _ = torch.cuda.mem_get_info(unet.device)
+    held = unet._workspace.numel() if getattr(unet, '_workspace', None) is not None else 0
+    if unet_mod.workspace_bytes(n, chunk_size) <= held:
+        return n
+    budget = held + free // 2
+    while n > 1 and unet_mod.workspace_bytes(n, chunk_size) > budget:
+        n = (n + 1) // 2
+    if unet_mod.workspace_bytes(n, chunk_size) > held + free:
+        raise _lib.IsgError(f'not enough device memory for one chunk of {tuple(chunk_size)} '
+                            f'({unet_mod.workspace_bytes(1, chunk_size) / 2**30:.2f} GiB of workspace)')
+    return n
 
 
 def get_device():
@@ -93,8 +111,9 @@ def predict_frame_device(unet, frame, chunk_size, margin, out=None, tables=None)
     st, lo, hi = tables if tables is not None else _chunk_tables(frame.shape, chunk_size, margin)
     if out is None:
         out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=frame.device)
-    for b in range(0, len(st), MAX_CHUNKS_PER_BATCH):
-        sl = slice(b, b + MAX_CHUNKS_PER_BATCH)
+    per = chunks_per_batch(unet, chunk_size, len(st))
+    for b in range(0, len(st), per):
+        sl = slice(b, b + per)
         unet.forward_chunks(frame, chunk_size, st[sl], lo[sl], hi[sl], out=out)
     return out
 

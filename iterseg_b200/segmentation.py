@@ -124,6 +124,7 @@ def affinity_watershed_for_chunks(input_volume, current_output, chunk_size, marg
         else:
             flat = current_output.reshape(-1)      # a view, like current_output.ravel() in :194
             flat[...] = labels.cpu().numpy().view(np.uint32).reshape(-1).astype(flat.dtype, copy=False)
+        unet.check_overflow()                      # the copy above waited for the frame
 
 
 # (addition) device-side counters of the most recent frame, for callers that need the number of
@@ -195,18 +196,42 @@ def _raise(err):
 
 def segmentation_loop(viewer, data, chunk_size, margin, output_labels, processing_function, config):
     """One 3-D frame at a time; yields the time point when done (segmentation.py:833-882),
-    including the warm restart: frames whose output is already non-zero are skipped."""
+    including the warm restart: frames whose output is already non-zero are skipped.
+
+    Additions that leave single-process results unchanged:
+    * tzyx series run through `iterseg_b200.pipeline.SeriesPipeline` (several frames in flight,
+      no host synchronisation on the compute streams);
+    * under an initialised `torch.distributed` job (one process per GPU) the frames of a series
+      are sharded `t = rank (mod world)` and every rank writes ITS frames into the shared output
+      store (a zarr store on a file system all ranks see: partial chunk writes are in place, so
+      ranks that share a t-chunk never touch each other's bytes); a single 3-D volume is sharded
+      into z-slabs (`iterseg_b200.slab`).  Opt out with config['shard'] = False;
+    * config['global_label_offsets'] = True makes label ids unique across the series (an
+      exclusive prefix of the per-frame label counts, one NCCL all-gather of R int64 per step;
+      the reference restarts at 1 in every frame, watershed.py:61-62)."""
+    from . import distributed as idist
+    rank, world = idist.world(config.get('process_group'))
+    if not config.get('shard', True):
+        rank, world = 0, 1
     ndim = data.ndim
     if ndim == 3:
+        if world > 1 and processing_function is affinity_watershed_for_chunks:
+            yield from _slab_volume(data, chunk_size, margin, output_labels, config)
+            return
         output = segment_single_volume(np.asarray(data).astype(np.float32), chunk_size, config,
                                        margin, processing_function)
         output_labels[...] = output
         yield 0
         return
-    if _can_pipeline(processing_function, config, data):
-        yield from _pipelined_series(data, chunk_size, margin, output_labels, config)
+    frames = idist.shard_frames(data.shape[0], rank, world)
+    core_kind = _pipeline_kind(processing_function, config, data)
+    if core_kind is not None:
+        yield from _pipelined_series(data, chunk_size, margin, output_labels, config, frames, core_kind,
+                                     processing_function)
         return
-    for t in range(data.shape[0]):
+    if config.get('global_label_offsets'):
+        raise NotImplementedError('global_label_offsets needs the pipelined series loop')
+    for t in frames:
         if np.any(output_labels[t]):
             continue
         input_volume = np.asarray(data[t]).astype(np.float32)
@@ -216,80 +241,165 @@ def segmentation_loop(viewer, data, chunk_size, margin, output_labels, processin
         yield t
 
 
-def _can_pipeline(processing_function, config, data):
-    return (processing_function is affinity_watershed_for_chunks and data.ndim == 4 and data.shape[0] > 1
-            and isinstance(config.get('unet'), unet_mod.UNet) and config.get('output_volume') is not None
-            and os.environ.get('ISG_NO_PIPELINE') is None)
+def _pipeline_kind(processing_function, config, data):
+    if data.ndim != 4 or os.environ.get('ISG_NO_PIPELINE') is not None:
+        return None
+    if processing_function is affinity_watershed_for_chunks and isinstance(config.get('unet'), unet_mod.UNet) \
+            and config.get('output_volume') is not None:
+        return 'affinity'
+    if processing_function is dog_blob_watershed_for_chunks and \
+            all(k in config for k in ('min_sigma', 'max_sigma', 'threshold')):
+        return 'dog'
+    return None
 
 
-def _pipelined_series(data, chunk_size, margin, output_labels, config):
-    """The frame loop of `segmentation_loop` for our own processing function: identical results
-    and yield order, but two frames in flight -- the host-side preparation (float32 cast, zero-
-    slice strip, `vol /= max`, segmentation.py:877,887-889) and the H2D copy of frame t+1 and the
-    U-Net of frame t+1 overlap the post stage and the D2H copy of frame t
-    (iterseg_b200/pipeline.py)."""
-    from .pipeline import FramePipeline
-    net = config['unet']
-    dev = net.device
-    lib = _lib.load()
-    pipe, pending = None, []          # pending: submitted time points, oldest first
-    scratch = torch.empty(64, dtype=torch.uint8, device=dev)
-    minmax = torch.zeros(2, dtype=torch.float32, device=dev)
+def _slab_volume(data, chunk_size, margin, output_labels, config):
+    """One 3-D volume under torch.distributed: z-slabs with halo planes (iterseg_b200.slab,
+    BASELINE.json configs[3]); every rank stores its own planes."""
+    from . import slab
+    vol = data if isinstance(data, np.ndarray) else np.asarray(data)
+    own, (z0, z1), n_labels = slab.segment_volume_slabs(
+        vol, config['unet'], tuple(int(c) for c in chunk_size), margin,
+        halo=int(config.get('slab_halo', 24)), group=config.get('process_group'))
+    LAST_COUNTS['n_labels'] = n_labels
+    output_labels[z0:z1, ...] = own.cpu().numpy()
+    yield 0
 
-    def prepare(t):
-        """Frame t on the device, normalised as segment_single_volume does (:887-889).  The cast,
-        the min / max and the division run on the device; only a frame that contains zeros takes
-        the reference's host route (slices that sum to zero are stripped first)."""
-        src = data[t]
-        if isinstance(src, np.ndarray) and src.dtype == np.float32 and src.flags.c_contiguous:
-            host = torch.from_numpy(src)
+
+def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, kind, processing_function):
+    """The frame loop of `segmentation_loop` for the two built-in processing functions: identical
+    results and yield order, but the host never waits for a compute stream (see
+    iterseg_b200/pipeline.py::SeriesPipeline): loader threads cast frame t+1.. into pinned
+    buffers and evaluate the warm-restart test (segmentation.py:875-877), the copy stream moves
+    frame t+1 and computes its min / max, the U-Net of frame t and the post stage of frame t-1
+    run on their streams, writer threads store finished frames."""
+    import collections
+    import concurrent.futures as cf
+    from . import distributed as idist
+    from .pipeline import DogCore, FramePipeline, SeriesPipeline
+    _lib.require_device()
+    dev = config['unet'].device if kind == 'affinity' else torch.device('cuda', torch.cuda.current_device())
+    shape = tuple(int(v) for v in data.shape[1:])
+    chunk = tuple(int(c) for c in chunk_size)
+    rank, world = idist.world(config.get('process_group')) if config.get('shard', True) else (0, 1)
+    want_offsets = bool(config.get('global_label_offsets'))
+    if want_offsets and kind != 'affinity':
+        raise NotImplementedError('global_label_offsets is implemented for the affinity U-Net watershed only')
+    n_steps = (int(data.shape[0]) + world - 1) // world        # lock-step count when offsets are global
+    offsets = idist.LabelOffsets(rank, world, dev, config.get('process_group')) if want_offsets else None
+
+    def make_pipe():
+        if kind == 'affinity':
+            core = FramePipeline(config['unet'], shape, chunk, margin)
         else:
-            host = torch.from_numpy(np.asarray(src).astype(np.float32))
-        frame = host.to(dev, non_blocking=True)
-        if frame.data_ptr() == host.data_ptr():               # never normalise the caller's array in place
-            frame = frame.clone()
-        with torch.cuda.device(dev):
-            _lib.check(lib.isg_frame_minmax(frame.data_ptr(), frame.numel(), minmax.data_ptr(), scratch.data_ptr(),
-                                            scratch.numel(), _lib.stream_ptr()), 'isg_frame_minmax')
-            if float(minmax[0].item()) == 0.0:
-                vol = remove_sum_zero_slices(np.asarray(src).astype(np.float32))
-                vol /= np.max(vol)
-                return torch.from_numpy(vol).to(dev)
-            _lib.check(lib.isg_frame_divide_by_max(frame.data_ptr(), frame.numel(), minmax.data_ptr(),
-                                                   _lib.stream_ptr()), 'isg_frame_divide_by_max')
-        return frame
+            core = DogCore(shape, dev, min_sigma=config['min_sigma'], max_sigma=config['max_sigma'],
+                           threshold=config['threshold'])
+        return SeriesPipeline(core)
 
-    def finish():
-        t_done = pending.pop(0)
-        lab, counts = pipe.collect()
+    pipe = make_pipe()
+    loaders = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-load')
+    writers = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-write')
+    SKIP = object()
+
+    def load(t):
+        if np.any(output_labels[t]):                             # warm restart (:875-876)
+            return SKIP
+        return pipe.load(data[t])
+
+    def store(t, o, host, direct):
+        pipe.outs[o]['ev_d2h'].synchronize()
+        if not direct:
+            output_labels[t, ...] = host.numpy()
+        pipe.release(o)
+        return t
+
+    def direct_dst(t):
+        """The caller's own memory for frame t when one D2H copy can land there."""
+        if isinstance(output_labels, np.ndarray) and output_labels.dtype in (np.int32, np.uint32):
+            dst = output_labels[t]
+            if dst.flags.c_contiguous and dst.shape == shape:
+                ten = torch.from_numpy(dst.view(np.int32))
+                if ten.is_pinned():
+                    return ten
+        return None
+
+    staged = collections.deque()        # (t, staging slot): H2D enqueued
+    running = collections.deque()       # t: U-Net enqueued
+    storing = collections.deque()       # writer futures, in frame order
+    steps_done = 0
+
+    def collect_one():
+        nonlocal steps_done
+        t = running.popleft()
+        dst = direct_dst(t)
+        on_counts = None
+        if offsets is not None:
+            on_counts = lambda counts: offsets.step(counts[0:1])      # noqa: E731
+            steps_done += 1
+        o, host, counts = pipe.collect(dst=dst, on_counts=on_counts)
         LAST_COUNTS['counts'] = counts
-        # only this frame's post stage has to be done: the next frame's U-Net keeps running
-        torch.cuda.current_stream(dev).wait_event(pipe.last_post_event)
-        crop = lab[1:-1, 1:-1, 1:-1]
-        dst = output_labels[t_done] if isinstance(output_labels, np.ndarray) else None
-        if dst is not None and dst.flags.c_contiguous and dst.dtype in (np.int32, np.uint32) and \
-                dst.shape == tuple(crop.shape):
-            torch.from_numpy(dst.view(np.int32)).copy_(crop)       # straight into the caller's array
-        else:
-            output_labels[t_done, ...] = crop.cpu().numpy().view(np.uint32)
-        return t_done
+        storing.append(writers.submit(store, t, o, host, dst is not None))
 
-    for t in range(data.shape[0]):
-        if np.any(output_labels[t]):                               # warm restart (:875-876)
-            continue
-        frame = prepare(t)
-        if pipe is not None and tuple(frame.shape) != pipe.shape:      # zero-slice strip changed the shape
-            while pending:
-                yield finish()
-            pipe = None
-        if pipe is None:
-            pipe = FramePipeline(net, tuple(frame.shape), tuple(int(c) for c in chunk_size), margin)
-        pipe.submit(frame)
-        pending.append(t)
-        if len(pending) == 2:
-            yield finish()
-    while pending:
-        yield finish()
+    def finished(block_if_more_than):
+        while storing and (storing[0].done() or len(storing) > block_if_more_than):
+            t_done = storing.popleft().result()
+            if kind == 'affinity':
+                config['unet'].check_overflow()                  # that frame's D2H has completed
+            yield t_done
+
+    def slow_zero_frame(t):
+        """A frame that contains zeros takes the reference's host route (segmentation.py:887-889:
+        slices that sum to zero are stripped before `vol /= max`); shapes may differ from the
+        series', so it runs outside the pipeline, after everything in flight has drained."""
+        while running:
+            collect_one()
+        yield from finished(0)
+        vol = np.asarray(data[t]).astype(np.float32)
+        output_labels[t, ...] = segment_single_volume(vol, chunk_size, config, margin, processing_function)
+        yield t
+
+    try:
+        todo = collections.deque(frames)
+        loading = collections.deque()       # (t, future)
+        while todo or loading or staged or running:
+            # keep two frames staged: their H2D copies run on the copy stream beside everything else
+            while (todo or loading) and len(staged) < 2:
+                while todo and len(loading) < 3:
+                    t = todo.popleft()
+                    loading.append((t, loaders.submit(load, t)))
+                t, fut = loading.popleft()
+                res = fut.result()
+                if res is SKIP:
+                    if want_offsets:
+                        raise NotImplementedError('a warm restart of a globally numbered series is not supported')
+                    continue
+                staged.append((t, pipe.h2d(res)))
+            if staged and len(running) < 2:                      # a U-Net slot is free
+                t, j = staged.popleft()
+                if pipe.submit(j):
+                    running.append(t)
+                else:
+                    if want_offsets:
+                        raise NotImplementedError('global_label_offsets with a frame that contains zeros')
+                    yield from slow_zero_frame(t)
+                continue
+            if running:
+                collect_one()
+            yield from finished(2)
+        while running:
+            collect_one()
+        if offsets is not None:                                  # ranks with fewer frames keep the lock-step
+            with torch.cuda.stream(pipe.core.s_post):
+                while steps_done < n_steps:
+                    offsets.step(None)
+                    steps_done += 1
+        yield from finished(0)
+        if offsets is not None:
+            LAST_COUNTS['global_total'] = offsets.total
+    finally:
+        loaders.shutdown(wait=False, cancel_futures=True)
+        writers.shutdown(wait=True)
+        torch.cuda.synchronize(dev)
 
 
 def segment_single_volume(input_volume, chunk_size, config, margin, processing_function):

@@ -28,6 +28,10 @@ contiguous range of z planes and the result is IDENTICAL to the single-device ru
     all-gather the sort keys of the kept seeds in their own planes, sort them, and every rank
     rewrites its local ids (own planes + halo objects alike) to the global ones.
 
+Not covered: a volume whose minimum is 0 -- the reference then strips all-zero slices before
+normalising (segmentation.py:887-888), which changes the global chunk grid; `segment_volume_slabs`
+all-reduces the minimum and raises NotImplementedError instead of silently differing.
+
 `SlabWorker` holds one rank's state and exposes the phases; `segment_volume_slabs` wires them
 to torch.distributed (NCCL), `segment_volume_emulated` runs R virtual ranks phase by phase on
 one GPU (tests, single-GPU bench).
@@ -123,15 +127,31 @@ class SlabWorker:
         s = self.slab
         return float(np.max(volume[s.z0:s.z1]))
 
-    def unet(self, volume, global_max):
-        """Own chunks of the global chunk list -> feature planes [z0, z1) (5, nz, Y, X)."""
+    def load_input(self, volume):
+        """H2D of the input planes this rank's chunks read (one contiguous copy; asynchronous when
+        `volume` is pinned).  Returns a device float32[2] = (min, max) of the OWN planes, to be
+        combined with MIN / MAX over the ranks (segmentation.py:887-889)."""
+        s = self.slab
+        sub = volume[s.in0:s.in1]
+        if isinstance(sub, torch.Tensor):
+            host = sub.to(torch.float32).contiguous()
+        else:
+            host = torch.from_numpy(np.ascontiguousarray(sub, dtype=np.float32))
+        self.frame = host.to(self.device, non_blocking=True)
+        if self.frame.data_ptr() == host.data_ptr():
+            self.frame = self.frame.clone()
+        own = self.frame[s.z0 - s.in0:s.z1 - s.in0]
+        return torch.stack([own.amin(), own.amax()])
+
+    def unet_device(self, gmax):
+        """Own chunks of the global chunk list -> feature planes [z0, z1) (5, nz, Y, X).
+        gmax: 1-element float32 device tensor, the maximum of the WHOLE volume."""
         s = self.slab
         st, lo, hi = self.tables
-        sub = np.ascontiguousarray(volume[s.in0:s.in1], dtype=np.float32)
-        frame = torch.from_numpy(sub).to(self.device)
         # vol /= max (segmentation.py:889): a true IEEE float32 division, tensor / tensor (torch
         # turns a division by a Python scalar into a multiplication by the reciprocal)
-        frame = frame / torch.tensor(np.float32(global_max), dtype=torch.float32, device=self.device)
+        frame = self.frame / gmax.reshape(()).to(self.device, torch.float32)
+        self.frame = None
         st_l = st[s.chunks].copy()
         st_l[:, 0] -= s.in0
         tabs = (np.ascontiguousarray(st_l), np.ascontiguousarray(lo[s.chunks]),
@@ -140,6 +160,11 @@ class SlabWorker:
         predict.predict_frame_device(self.net, frame, self.chunk_size, self.margin, out=out, tables=tabs)
         self.feats_own = out[:, s.z0 - s.in0:s.z1 - s.in0].contiguous()
         return self.feats_own
+
+    def unet(self, volume, global_max):
+        """load_input + unet_device with a host-side global maximum (emulated ranks, tests)."""
+        self.load_input(volume)
+        return self.unet_device(torch.tensor([np.float32(global_max)], dtype=torch.float32, device=self.device))
 
     def set_features(self, feats_own):
         """Bypass the U-Net (tests / feature maps from elsewhere): planes [z0, z1)."""
@@ -226,9 +251,19 @@ class SlabWorker:
         keys = _u64_buf(max_seeds, self.device)
         slab = {'aff_div': [float(c) for c in chan_max.tolist()], 'own_z0': self.own0, 'own_z1': self.own1,
                 'open_faces': (1 if self.h_lo else 0) | (2 if self.h_hi else 0), 'seed_keys': keys}
-        seeds, counts, mask, _ = watershed.segment_features_device(
-            self.feats_ext, self.labels_ext, aff, cent, tch, scale=self.scale, absolute_thresh=thr,
-            max_seeds=max_seeds, slab=slab)
+        # the ordered flood's compact arenas are sized for a quarter of the voxels lying in
+        # multi-seed components (a real mask covers a few per cent); if a slab needs more, the call
+        # fails loudly and is repeated with the worst-case workspace
+        kw = dict(scale=self.scale, absolute_thresh=thr, max_seeds=max_seeds, slab=slab)
+        try:
+            seeds, counts, mask, _ = watershed.segment_features_device(
+                self.feats_ext, self.labels_ext, aff, cent, tch, max_flood_nodes=(Z * Y * X) // 4, **kw)
+        except _lib.IsgError as e:
+            if e.status != _lib.ISG_ERR_WORKSPACE:
+                raise
+            self.labels_ext.zero_()
+            seeds, counts, mask, _ = watershed.segment_features_device(
+                self.feats_ext, self.labels_ext, aff, cent, tch, **kw)
         c = counts.cpu().numpy()
         if c[4]:
             raise HaloTooSmall(f'rank {self.rank}: an object that reaches planes [{self.slab.z0},{self.slab.z1}) '
@@ -284,6 +319,8 @@ def segment_volume_emulated(volume, net, chunk_size, margin, world, halo=24, fea
     shape = tuple(volume.shape) if volume is not None else tuple(features.shape[1:])
     ws = [SlabWorker(net, shape, chunk_size, margin, r, world, halo=halo, **kw) for r in range(world)]
     if features is None:
+        if float(np.min(volume)) == 0.0:
+            raise NotImplementedError('the volume contains zeros (remove_sum_zero_slices is not sharded)')
         gmax = max(w.local_input_max(volume) for w in ws)
         for w in ws:
             w.unet(volume, gmax)
@@ -317,9 +354,18 @@ def segment_volume_slabs(volume, net, chunk_size, margin, halo=24, group=None, f
     w = SlabWorker(net, shape, chunk_size, margin, rank, world, halo=halo, **kw)
     dev = w.device
     if features is None:
-        m = torch.tensor([w.local_input_max(volume)], dtype=torch.float64, device=dev)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-        w.unet(volume, float(m.item()))
+        mm = w.load_input(volume)                       # H2D + device min / max of the own planes
+        lo, hi = mm[0:1].clone(), mm[1:2].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        if float(lo.item()) == 0.0:
+            # segment_single_volume strips the slices that sum to zero when min() == 0
+            # (segmentation.py:887-888): that changes the chunk grid of the WHOLE volume
+            raise NotImplementedError(
+                'the volume contains zeros: the reference strips all-zero slices first '
+                '(remove_sum_zero_slices), which the slab-sharded path does not implement -- strip '
+                'them before sharding or run the volume on one device')
+        w.unet_device(hi)
     else:
         w.set_features(torch.as_tensor(features)[:, w.slab.z0:w.slab.z1])
     # halo planes to / from the neighbours (NCCL point-to-point over NVLink)

@@ -189,3 +189,70 @@ def structured_state_dict(seed=0, noise=0.25):
         ordered[name + '.weight'] = torch.from_numpy(w)
         ordered[name + '.bias'] = torch.from_numpy(bb)
     return ordered
+
+
+class JitteredSeries:
+    """A tzyx float32 series of `n_frames` synthetic platelet frames that costs `n_base` frame
+    renderings instead of n_frames (BASELINE.json configs[2]: 192 frames; rendering one frame
+    takes ~1 s of host time): frame t is base frame t % n_base rolled by (0, 3k, 5k) voxels with
+    k = t // n_base -- the platelets drift frame to frame, every frame is distinct, min > 0.
+    Only the frames listed in `own` are materialised (a rank of a frame-sharded run holds its own
+    frames), in pinned host memory when `pin` is set.  Duck-types what `segmentation_loop`
+    reads: .shape, .ndim, .dtype, data[t]."""
+
+    def __init__(self, n_frames, shape=(33, 512, 512), n_base=4, seed0=0, own=None, pin=False):
+        self.shape = (int(n_frames),) + tuple(int(s) for s in shape)
+        self.ndim = 4
+        self.dtype = np.dtype(np.float32)
+        self.n_base = int(n_base)
+        own = range(n_frames) if own is None else own
+        base = {}
+        self.frames = {}
+        buf = None
+        own = list(own)
+        if pin:
+            import torch
+            self._pinned = torch.empty((len(own),) + self.shape[1:], dtype=torch.float32).pin_memory()
+            buf = self._pinned.numpy()
+        for i, t in enumerate(own):
+            b = t % self.n_base
+            if b not in base:
+                base[b] = platelet_frame(self.shape[1:], seed=seed0 + b)
+            k = t // self.n_base
+            fr = np.roll(base[b], (3 * k, 5 * k), axis=(1, 2)) if k else base[b]
+            if buf is not None:
+                buf[i] = fr
+                self.frames[t] = buf[i]
+            else:
+                self.frames[t] = np.ascontiguousarray(fr)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, t):
+        if isinstance(t, tuple):
+            return self.frames[int(t[0])][t[1:]]
+        return self.frames[int(t)]
+
+
+def big_volume_planes(shape, z0, z1, tile=(32, 512, 512), seed0=1000, n_base=3, out=None):
+    """Planes [z0, z1) of the synthetic big volume of BASELINE.json configs[3] (256 x 2048 x 2048,
+    same platelet density): a mosaic of `n_base` rendered (tile z + 1, tile y, tile x) blocks,
+    each mosaic cell a different block / in-plane roll, the z tiling shifted by half a tile so
+    that objects straddle the z-slab borders of an 8-way split.  Deterministic in (shape, seed0):
+    every rank renders the planes it needs and they fit together."""
+    Z, Y, X = (int(s) for s in shape)
+    tz, ty, tx = tile
+    base = [platelet_frame((tz, ty, tx), seed=seed0 + b) for b in range(n_base)]
+    planes = np.empty((z1 - z0, Y, X), np.float32) if out is None else out
+    for z in range(z0, z1):
+        zz = z + tz // 2
+        cz, lz = zz // tz, zz % tz
+        for iy in range(0, Y, ty):
+            for ix in range(0, X, tx):
+                cell = cz * 131 + (iy // ty) * 17 + (ix // tx) * 5
+                src = base[cell % n_base][lz]
+                sh = (7 * cell) % ty, (11 * cell) % tx
+                blk = np.roll(src, sh, axis=(0, 1))
+                planes[z - z0, iy:iy + ty, ix:ix + tx] = blk[:min(ty, Y - iy), :min(tx, X - ix)]
+    return planes

@@ -41,33 +41,33 @@ class ConvModule(nn.Module):
 
 
 class _Plan:
-    """isg_unet_plan + the workspace it points into."""
+    """isg_unet_plan: the geometry (frame extent, chunk extent, chunk count) over the U-Net's
+    shared workspace.  The chunk tables are per-call data (`set_chunks`)."""
 
-    def __init__(self, unet, frame_shape, chunk_shape, starts, crop_lo, crop_hi):
+    def __init__(self, unet, frame_shape, chunk_shape, n_chunks, workspace):
         lib = _lib.load()
-        self.n = len(starts)
+        self.n = int(n_chunks)
         self.frame_shape = tuple(int(s) for s in frame_shape)
         self.chunk_shape = tuple(int(s) for s in chunk_shape)
         cz, cy, cx = self.chunk_shape
-        nbytes = lib.isg_unet_workspace_bytes(self.n, cz, cy, cx)
-        if nbytes == 0:
-            raise ValueError(
-                f'chunk shape {self.chunk_shape} is not valid for this U-Net (z must be even, y/x '
-                'must survive four poolings and the decoder crops, e.g. (10, 256, 256))')
-        dev = unet.device
-        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        st = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 3)
-        lo = np.ascontiguousarray(crop_lo, dtype=np.int32).reshape(-1, 3)
-        hi = np.ascontiguousarray(crop_hi, dtype=np.int32).reshape(-1, 3)
+        self.workspace = workspace                     # keeps the tensor alive as long as the plan
         self.packed = unet.packed_weights()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(unet.device):
             self.ptr = lib.isg_unet_plan_create(
-                self.packed.data_ptr(), self.n, cz, cy, cx, *self.frame_shape,
-                st.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                self.packed.data_ptr(), self.n, cz, cy, cx, *self.frame_shape, None, None, None,
                 self.workspace.data_ptr(), self.workspace.numel())
         if not self.ptr:
             raise _lib.IsgError('isg_unet_plan_create: ' + lib.isg_last_error().decode())
         self.flops = lib.isg_unet_plan_flops(self.ptr)
+
+    def set_chunks(self, starts, crop_lo, crop_hi):
+        st = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 3)
+        lo = np.ascontiguousarray(crop_lo, dtype=np.int32).reshape(-1, 3)
+        hi = np.ascontiguousarray(crop_hi, dtype=np.int32).reshape(-1, 3)
+        if not (len(st) == len(lo) == len(hi) == self.n):
+            raise ValueError(f'plan of {self.n} chunks got tables of {len(st)}, {len(lo)}, {len(hi)} rows')
+        _lib.check(_lib.load().isg_unet_plan_set_chunks(self.ptr, st.ctypes.data, lo.ctypes.data, hi.ctypes.data),
+                   'isg_unet_plan_set_chunks')
 
     def __del__(self):
         try:
@@ -76,6 +76,12 @@ class _Plan:
                 self.ptr = None
         except Exception:
             pass
+
+
+def workspace_bytes(n_chunks, chunk_shape):
+    """Activation workspace of one forward_chunks call (0: the chunk shape is not valid)."""
+    cz, cy, cx = (int(c) for c in chunk_shape)
+    return int(_lib.load().isg_unet_workspace_bytes(int(n_chunks), cz, cy, cx))
 
 
 class UNet(nn.Module):
@@ -97,7 +103,8 @@ class UNet(nn.Module):
         for name, c, k in UPS:
             setattr(self, name, nn.ConvTranspose3d(c, c, kernel_size=k, stride=k, groups=c))
         self._packed = None
-        self._plans = {}
+        self._plans = {}              # (frame shape, chunk shape, n chunks) -> _Plan, least recently used first
+        self._workspace = None        # ONE activation workspace shared by all plans (they run in stream order)
 
     # ---- weights -------------------------------------------------------------------
     @property
@@ -107,6 +114,7 @@ class UNet(nn.Module):
     def _invalidate(self):
         self._packed = None
         self._plans = {}
+        self._workspace = None
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -147,29 +155,72 @@ class UNet(nn.Module):
         return packed
 
     # ---- execution -----------------------------------------------------------------
-    def plan(self, frame_shape, chunk_shape, starts, crop_lo, crop_hi):
-        key = (tuple(frame_shape), tuple(chunk_shape), np.asarray(starts).tobytes(),
-               np.asarray(crop_lo).tobytes(), np.asarray(crop_hi).tobytes())
-        p = self._plans.get(key)
+    MAX_PLANS = 8
+
+    def plan(self, frame_shape, chunk_shape, n_chunks):
+        """The plan for `n_chunks` chunks of `chunk_shape` cut from a frame of `frame_shape`.
+        All plans of a network share one workspace, sized for the largest request so far; when it
+        has to grow, the plans that point into the old block are dropped (the old block stays
+        alive until the kernels already enqueued on the current stream are done: torch's caching
+        allocator only hands it out again in stream order, and forward_chunks records every
+        stream that used it)."""
+        key = (tuple(int(v) for v in frame_shape), tuple(int(v) for v in chunk_shape), int(n_chunks))
+        p = self._plans.pop(key, None)
         if p is None:
-            if len(self._plans) >= 4:
+            need = workspace_bytes(n_chunks, chunk_shape)
+            if need == 0:
+                raise ValueError(
+                    f'chunk shape {key[1]} is not valid for this U-Net (z must be even, y/x '
+                    'must survive four poolings and the decoder crops, e.g. (10, 256, 256))')
+            if self._workspace is None or self._workspace.numel() < need:
+                held = self._workspace.numel() if self._workspace is not None else 0
+                free, _ = torch.cuda.mem_get_info(self.device)
+                if need > free + held:
+                    torch.cuda.empty_cache()                       # blocks torch caches but does not use
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                if need > free + held:
+                    raise _lib.IsgError(
+                        f'the U-Net workspace for {n_chunks} chunks of {key[1]} needs {need / 2**30:.1f} GiB, '
+                        f'{(free + held) / 2**30:.1f} GiB are free on {self.device}: use fewer chunks per batch')
                 self._plans.clear()
-            p = _Plan(self, frame_shape, chunk_shape, starts, crop_lo, crop_hi)
-            self._plans[key] = p
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            while len(self._plans) >= self.MAX_PLANS:
+                self._plans.pop(next(iter(self._plans)))          # least recently used
+            p = _Plan(self, key[0], key[1], key[2], self._workspace)
+        self._plans[key] = p                                       # most recently used last
         return p
 
     def forward_chunks(self, frame, chunk_shape, starts, crop_lo, crop_hi, out=None):
         """frame (Z,Y,X) float32 CUDA tensor -> (5,Z,Y,X) float32: the cropped interior of
         every chunk's prediction is placed into `out` (process_chunks, predict.py:64-96)."""
         assert frame.is_cuda and frame.dtype == torch.float32 and frame.is_contiguous()
-        p = self.plan(frame.shape, chunk_shape, starts, crop_lo, crop_hi)
+        p = self.plan(frame.shape, chunk_shape, len(starts))
+        p.set_chunks(starts, crop_lo, crop_hi)
         if out is None:
             out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=frame.device)
         with torch.cuda.device(frame.device):
+            p.workspace.record_stream(torch.cuda.current_stream())
             rc = _lib.load().isg_unet_forward_chunks(p.ptr, frame.data_ptr(), out.data_ptr(),
                                                      _lib.stream_ptr())
         _lib.check(rc, 'isg_unet_forward_chunks')
         return out
+
+    def check_overflow(self):
+        """Raise IsgError (status ISG_ERR_OVERFLOW) if a COMPLETED forward pass left the fp16 range
+        of the pre-BatchNorm activations (include/iterseg_b200.h, "fp16 range guard").  Does not
+        synchronise: call it after waiting for the features or the labels."""
+        lib = _lib.load()
+        for p in self._plans.values():
+            if lib.isg_unet_plan_overflowed(p.ptr):
+                with torch.cuda.device(self.device):
+                    lib.isg_unet_plan_clear_overflow(p.ptr, _lib.stream_ptr())
+                err = _lib.IsgError(
+                    'the U-Net overflowed the fp16 range of its pre-BatchNorm activations: the feature volume of '
+                    'that forward pass is invalid (filters are prescaled per output channel, so this means '
+                    'BatchNorm / transposed-convolution parameters of extreme magnitude)')
+                err.status = _lib.ISG_ERR_OVERFLOW
+                raise err
 
     def forward(self, x):
         """x: (1,1,D,H,W) -> (1,5,D,H,W) float32 on the device, like the reference's forward
@@ -185,13 +236,16 @@ class UNet(nn.Module):
         shape = tuple(frame.shape)
         zeros = np.zeros((1, 3), np.int32)
         out = self.forward_chunks(frame, shape, zeros, zeros, np.asarray([shape], np.int32))
+        torch.cuda.current_stream(self.device).synchronize()
+        self.check_overflow()
         return out[None]
 
     def debug_conv_output(self, frame, chunk_shape, starts, crop_lo, crop_hi, name, chunk=0):
         """Raw (pre-BatchNorm, bias-free) output of convolution `name` for one chunk as
         (Cout, D, H, W) float32 -- parity tests only."""
         lib = _lib.load()
-        p = self.plan(frame.shape, chunk_shape, starts, crop_lo, crop_hi)
+        p = self.plan(frame.shape, chunk_shape, len(starts))
+        p.set_chunks(starts, crop_lo, crop_hi)
         mod, conv = name.split('.')
         cout = getattr(getattr(self, mod), conv).out_channels
         level = {'c0': 0, 'c1': 1, 'c2': 2, 'c3': 3, 'c4': 4, 'c5_0': 3, 'c6_0': 2, 'c7_0': 1, 'c8_0': 0}[mod]

@@ -77,7 +77,8 @@ def post_params(affinities_channels=(0, 1, 2), centroids_channel=4, thresholding
 
 def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centroids_channel=4,
                             thresholding_channel=3, scale=None, absolute_thresh=None,
-                            max_seeds=None, min_area=10, max_area=10000000, slab=None):
+                            max_seeds=None, min_area=10, max_area=10000000, slab=None,
+                            max_flood_nodes=None):
     """Device-resident core of segment_output_image.
 
     feats  : (C,Z,Y,X) float32 CUDA tensor (not modified)
@@ -87,6 +88,10 @@ def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centro
     halo_violation, 0, 0, 0).
     slab: None, or a dict for one z-slab of a larger volume (iterseg_b200/slab.py):
     aff_div (3 floats), own_z0, own_z1, open_faces, seed_keys (int64 CUDA tensor [max_seeds]).
+    max_flood_nodes: None = a workspace for the worst case (every voxel inside a multi-seed mask
+    component, ~200 B per voxel); a number sizes the ordered flood's compact arenas for at most
+    that many such voxels (isg_post_workspace_bytes_capped) -- a frame that needs more raises
+    IsgError with status ISG_ERR_WORKSPACE and must be re-run on zeroed labels.
     """
     lib = _lib.load()
     assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
@@ -106,8 +111,11 @@ def segment_features_device(feats, labels, affinities_channels=(0, 1, 2), centro
         keys = slab['seed_keys']
         assert keys.is_cuda and keys.dtype == torch.int64 and keys.numel() >= max_seeds
         p.seed_keys_out = keys.data_ptr()
-    nbytes = lib.isg_post_workspace_bytes(Z, Y, X, max_seeds)
-    ws = _workspace('post', (Z, Y, X, max_seeds), nbytes, dev)
+    if max_flood_nodes is None:
+        nbytes = lib.isg_post_workspace_bytes(Z, Y, X, max_seeds)
+    else:
+        nbytes = lib.isg_post_workspace_bytes_capped(Z, Y, X, max_seeds, max(int(max_flood_nodes), 1))
+    ws = _workspace('post', (Z, Y, X, max_seeds, max_flood_nodes), nbytes, dev)
     mask = torch.empty((Z + 2, Y + 2, X + 2), dtype=torch.uint8, device=dev)
     seeds = torch.empty(max_seeds, dtype=torch.int64, device=dev)
     counts = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -268,24 +276,25 @@ def raveled_affinity_watershed(image_raveled, marker_coords, offsets, mask, outp
     seeds = np.asarray(marker_coords, dtype=np.int64).reshape(-1)
     seeds_d = torch.from_numpy(seeds).to(dev)
     out_np = np.asarray(output)
-    # the seed labels are already in `output`; the kernel re-writes the same values
+    # Seed voxels carry the caller's labels (watershed.py:61-62); any OTHER voxel that is non-zero
+    # on entry is never claimed (the reference tests `output[neighbor_index]`, :150) and keeps its
+    # value.  The kernel labels seed i with i+1, so the flood runs on a copy whose seed voxels
+    # are cleared, and the caller's seed labels are restored through a LUT afterwards -- only on
+    # voxels the flood itself wrote (`claimed`, taken BEFORE the flood modifies `work`).
     labels_d = torch.from_numpy(out_np.astype(np.uint32).view(np.int32).reshape(shape_p)).to(dev)
-    pre = labels_d.clone()
+    work = labels_d.clone()
     if len(seeds):
-        pre.view(-1)[seeds_d] = 0
-    # voxels labelled on entry that are not seeds are barriers for the flood
-    labels_in = pre
+        work.view(-1)[seeds_d] = 0
+    claimable = (work == 0).cpu().numpy().reshape(-1)
     ones = torch.ones(3, dtype=torch.float32, device=dev)
-    _run_flood(aff_d, 0, ones, mask_d, seeds_d, labels_in, shape_p, None)
-    res = labels_in.cpu().numpy().view(np.uint32).reshape(-1)
+    _run_flood(aff_d, 0, ones, mask_d, seeds_d, work, shape_p, None)
+    res = work.cpu().numpy().view(np.uint32).reshape(-1)
     if len(seeds):
-        # keep whatever labels the caller had put on the seed voxels
         lab_seed = out_np.reshape(-1)[seeds].astype(np.uint32)
         canon = np.arange(1, len(seeds) + 1, dtype=np.uint32)
         if not np.array_equal(lab_seed, canon):
             lut = np.zeros(len(seeds) + 1, dtype=np.uint32)
             lut[1:] = lab_seed
-            flooded = pre.cpu().numpy().reshape(-1) == 0
-            res = np.where(flooded, lut[np.minimum(res, len(seeds))], res)
+            res = np.where(claimable, lut[np.minimum(res, len(seeds))], res)
     output[...] = res.astype(out_np.dtype, copy=False).reshape(out_np.shape)
     return output

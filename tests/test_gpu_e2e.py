@@ -78,6 +78,24 @@ def test_end_to_end_vs_cpu_oracle(net, frame):
     assert f1 >= 0.99, f1
 
 
+def test_end_to_end_gate_on_a_full_baseline_frame(net):
+    """The same gate at the size BASELINE.json quotes (configs[0]/[1]): one 33x512x512 frame, 36 chunks of
+    (10,256,256) margin (1,64,64).  Reference arm: fp32 torch-CPU U-Net (train-mode BN) on all 36
+    chunks + the scipy/numpy post stage + the heap flood."""
+    from iterseg_b200 import synth
+    from oracle import metrics, post, unet_ref
+    vol = synth.platelet_frame((33, 512, 512), seed=0)
+    sd = synth.structured_state_dict(0)
+    feats = unet_ref.predict_frame(vol, sd)
+    seg_o, _, _ = post.segment_output_image(feats)
+    seg_g = _segment(net, vol)[1:-1, 1:-1, 1:-1]
+    assert seg_o.max() > 1000
+    vi = sum(metrics.variation_of_information(seg_o, seg_g))
+    f1 = metrics.matched_f1(seg_o, seg_g, 0.5)
+    assert vi <= 0.01, vi
+    assert f1 >= 0.99, f1
+
+
 def test_segment_data_timeseries_zarr_and_warm_restart(net, tmp_path):
     from iterseg_b200 import _dock_widgets, synth, viewer
     shape = (10, 256, 256)

@@ -117,6 +117,30 @@ def test_raveled_entry_point(ws, scenes):
     assert np.array_equal(output.reshape(shape), want)
 
 
+def test_raveled_entry_point_keeps_caller_labels(ws, scenes):
+    """the seeds carry whatever labels the caller put into `output` (watershed.py:61-62
+    is the caller's business) and pre-labelled non-seed voxels are barriers that keep their value
+    -- also when that value collides with 1..N."""
+    from oracle import flood as oflood
+    aff, seeds, mask = (scenes[f'ties4_{k}'] for k in ('aff', 'seeds', 'mask'))
+    shape = mask.shape
+    raveled = np.stack([a.ravel() for a in aff])
+    flat = oflood.ravel_seeds(seeds, shape)
+    table = oflood.neighbor_table(shape)
+    rng = np.random.default_rng(5)
+    output = np.zeros(mask.size, np.uint32)
+    output[flat] = rng.permutation(len(flat)).astype(np.uint32) * 3 + 7        # not 1..N, not sorted
+    free = np.flatnonzero(mask.ravel() & (output == 0))
+    barrier = rng.choice(free, size=max(4, len(free) // 50), replace=False)
+    output[barrier] = rng.integers(1, len(flat) + 1, len(barrier)).astype(np.uint32)   # collide with 1..N
+    want = output.copy()
+    oflood.raveled_flood_c(raveled, flat, table, mask.ravel(), want)
+    got = output.copy()
+    ws.raveled_affinity_watershed(raveled, flat, table, mask.ravel(), got)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[barrier], output[barrier])
+
+
 def test_segment_output_image_golden(ws, golden_dir):
     g = np.load(os.path.join(golden_dir, 'post_small.npz'))
     feats = g['feats'].astype(np.float32)

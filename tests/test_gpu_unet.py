@@ -100,3 +100,46 @@ def test_state_dict_roundtrip(tmp_path, net):
     u = predict.load_unet(path)
     x = torch.rand(1, 1, 4, 32, 32)
     assert torch.equal(u(x), net(x))
+
+
+def test_fp16_range_guard_filter_scale(net):
+    """VERDICT r1 item 7.  The reference's output does not depend on the scale of a filter (a
+    train-mode BatchNorm follows every convolution), its fp32 arithmetic does not care either; fp16
+    storage of the pre-BatchNorm activations would overflow at 65504.  Filters are therefore
+    prescaled per output channel at pack time: weights x 2^12 (one layer), x 2^-14 (another) and a
+    single huge channel must still match the fp32 oracle within the 1e-2 gate."""
+    from iterseg_b200 import unet as unet_mod
+    from oracle import unet_ref
+    sd = {k: v.clone() for k, v in unet_ref.synth_state_dict(0).items()}
+    sd['c1.conv1.weight'] *= 2.0 ** 12
+    sd['c6_0.conv0.weight'] *= 2.0 ** -14
+    sd['c2.conv0.weight'][3] *= 2.0 ** 15
+    n2 = unet_mod.UNet()
+    n2.load_state_dict(sd)
+    n2.cuda()
+    x = np.random.default_rng(2).random((1, 1, 6, 48, 48), dtype=np.float32)
+    want = unet_ref.unet_forward(torch.from_numpy(x), sd)
+    got = n2(torch.from_numpy(x)).cpu()
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= TOL
+
+
+def test_fp16_overflow_is_refused_loudly(monkeypatch):
+    """Without the prescale (diagnosis switch) the same weights overflow fp16: the path must raise,
+    never hand out inf / NaN features silently; after the error the plan is usable again."""
+    from iterseg_b200 import _lib, unet as unet_mod
+    from oracle import unet_ref
+    monkeypatch.setenv('ISG_NO_WEIGHT_PRESCALE', '1')
+    sd = {k: v.clone() for k, v in unet_ref.synth_state_dict(0).items()}
+    sd['c1.conv1.weight'] *= 2.0 ** 14
+    n2 = unet_mod.UNet()
+    n2.load_state_dict(sd)
+    n2.cuda()
+    x = torch.from_numpy(np.random.default_rng(2).random((1, 1, 6, 48, 48), dtype=np.float32))
+    with pytest.raises(_lib.IsgError) as ei:
+        n2(x)
+    assert ei.value.status == _lib.ISG_ERR_OVERFLOW
+    monkeypatch.delenv('ISG_NO_WEIGHT_PRESCALE')
+    n2.load_state_dict(unet_ref.synth_state_dict(0))          # re-pack with the prescale
+    n2.cuda()
+    assert torch.isfinite(n2(x)).all()

@@ -171,3 +171,85 @@ def test_plan_slabs_partitions_chunks_exactly_once():
     assert max(sizes) - min(sizes) <= 8 and len(slabs[0].chunks) * 8 >= 7200 * 0.9
     with pytest.raises(ValueError):
         slab.plan_slabs((33, 512, 512), (10, 256, 256), (1, 64, 64), 8)
+
+
+OFFSETS_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from iterseg_b200 import _io, distributed as d
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+assert d.world() == (rank, world)
+T, shape = 7, (3, 8, 6)
+mine = d.shard_frames(T, rank, world)
+n_steps = (T + world - 1) // world
+counts = {t: 10 * t + 1 for t in range(T)}          # pretend frame t holds 10t+1 labels
+off = d.LabelOffsets(rank, world, torch.device('cpu'))
+store = _io.open_zarr(%(store)r, shape=(T,) + shape, chunks=(4, 2, 8), dtype=np.int32)   # t-chunk of 4 frames
+got = {}
+for s in range(n_steps):
+    t = s * world + rank
+    o = off.step(torch.tensor([counts[t]]) if t < T else None)     # every rank, every step
+    if t < T:
+        got[t] = int(o.item())
+        store[t, ...] = np.full(shape, got[t] + 1, np.int32)       # ranks share t-chunk files
+want = np.concatenate([[0], np.cumsum([counts[t] for t in range(T)])])
+assert all(got[t] == want[t] for t in mine), (got, want)
+assert int(off.total.item()) == want[-1]
+dist.barrier()
+if rank == 0:
+    a = np.asarray(_io.open_zarr(%(store)r))
+    for t in range(T):
+        assert (a[t] == want[t] + 1).all(), (t, a[t].ravel()[:4], want[t] + 1)
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write('rank ' + str(rank) + ' ok\n')
+sys.stdout.flush()
+'''
+
+
+def test_running_label_offsets_and_shared_store_two_ranks_gloo(tmp_path):
+    """World-size-2 run of the host logic behind the frame-sharded series (BASELINE configs[2]):
+    frames t = rank (mod 2), one all-gather per step giving the exclusive prefix of the label
+    counts, and both ranks writing their frames into the SAME t-chunk files of one zarr store."""
+    script = tmp_path / 'worker2.py'
+    script.write_text(OFFSETS_WORKER % {'root': ROOT, 'store': str(tmp_path / 'lab')})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29613', str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
+
+
+def test_label_store_reopens_with_its_own_metadata(tmp_path):
+    """ADVICE r1: an existing store keeps its shape / chunks / dtype on re-open (warm restart with a
+    different chunk_size), a shape mismatch raises, and a compressed store is refused."""
+    from iterseg_b200 import _io
+    a = _io.open_zarr(str(tmp_path / 's'), shape=(6, 4, 10, 12), chunks=(2, 4, 5), dtype=np.int32)
+    v = np.arange(4 * 10 * 12, dtype=np.int32).reshape(4, 10, 12)
+    a[3, ...] = v
+    b = _io.open_zarr(str(tmp_path / 's'), shape=(6, 4, 10, 12), chunks=(1, 2, 2), dtype=np.int64)
+    assert b.chunks == (2, 4, 5, 12) and b.dtype == np.int32
+    assert np.array_equal(b[3], v) and not b[2].any()
+    with pytest.raises(ValueError):
+        _io.open_zarr(str(tmp_path / 's'), shape=(5, 4, 10, 12), chunks=(2, 4, 5))
+    meta_fn = tmp_path / 's' / '.zarray'
+    meta = json.loads(meta_fn.read_text())
+    meta['compressor'] = {'id': 'blosc', 'cname': 'lz4', 'clevel': 5, 'shuffle': 1, 'blocksize': 0}
+    meta_fn.write_text(json.dumps(meta))
+    with pytest.raises(NotImplementedError):
+        _io.open_zarr(str(tmp_path / 's'), shape=(6, 4, 10, 12), chunks=(2, 4, 5))
+
+
+def test_series_and_volume_synth_are_rank_consistent():
+    from iterseg_b200 import synth
+    a = synth.JitteredSeries(12, (6, 40, 40), n_base=2, own=[1, 5, 9])
+    b = synth.JitteredSeries(12, (6, 40, 40), n_base=2, own=range(12))
+    assert a.shape == (12, 6, 40, 40) and a.ndim == 4
+    for t in (1, 5, 9):
+        assert np.array_equal(a[t], b[t]) and a[t].min() > 0
+    assert not np.array_equal(b[1], b[3])                 # same base frame, different jitter
+    p = synth.big_volume_planes((40, 96, 96), 10, 14, tile=(8, 32, 32))
+    q = synth.big_volume_planes((40, 96, 96), 0, 40, tile=(8, 32, 32))
+    assert np.array_equal(p, q[10:14]) and q.min() > 0
