@@ -263,7 +263,11 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
     mem = torch.zeros((n_frames,) + FRAME, dtype=torch.int32).pin_memory() if world == 1 else None
     if mem is not None:
         dt = timed(mem.numpy())
-        rec['in_memory'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3}
+        tm = dict(segmentation.LAST_COUNTS.get('timing', {}))
+        rec['in_memory'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3,
+                            'setup_s': tm.get('setup_s'), 'first_frame_s': tm.get('first_frame_s'),
+                            'steady_ms_per_frame': ((tm['last_frame_s'] - tm['first_frame_s']) / max(tm['frames'] - 1, 1) * 1e3
+                                                    if tm.get('frames', 0) > 1 else None)}
         total = int(segmentation.LAST_COUNTS['global_total'].item())
         rec['labels_total'] = total
         rec['labels_global_ok'] = bool(int(mem[-1].max()) == total and int(mem[0].max()) < int(mem[-1].max()))
@@ -280,7 +284,11 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
         arr = _io.open_zarr(os.path.join(store, '0'), shape=data.shape, chunks=CHUNK, dtype=np.int32)
     dt = timed(arr)
     total = int(segmentation.LAST_COUNTS['global_total'].item())
+    tm = dict(segmentation.LAST_COUNTS.get('timing', {}))
     rec['zarr'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3,
+                   'setup_s': tm.get('setup_s'), 'first_frame_s': tm.get('first_frame_s'),
+                   'steady_ms_per_frame': ((tm['last_frame_s'] - tm['first_frame_s']) / max(tm['frames'] - 1, 1) * 1e3
+                                           if tm.get('frames', 0) > 1 else None),
                    'store': 'OME-zarr v0.4 labels, int32, chunks (10,33,256,512), raw chunks, /tmp'}
     rec['labels_total'] = total
     if rank == 0:
@@ -442,7 +450,7 @@ def run_gpu(args, rank, local_rank, world):
     # through `segmentation.segmentation_loop`, the frame loop behind `segment_data` /
     # `affinity_unet_watershed`; with world > 1 every rank runs its own K frames (weak scaling,
     # like `value`) and the label ids are made global by the per-step all-gather
-    n_e2e = max(args.steps, 4)
+    n_e2e = max(4 * args.steps, 16)             # long enough that pipeline fill / drain is amortised
     series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
     out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
     config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False}

@@ -235,7 +235,7 @@ size_t isg_unet_workspace_bytes(int n_chunks, int cz, int cy, int cx);
  * exactly as make_chunks returns them (predict.py:38-61).  They may be NULL at creation and
  * (re)set at any time with isg_unet_plan_set_chunks: a plan is a (frame extent, chunk extent,
  * chunk count) geometry over a workspace, the tables are per-call data.  The tables are copied
- * into pinned memory owned by the plan and uploaded by the NEXT isg_unet_forward_chunks with
+ * into pinned memory owned by the plan and uploaded by EVERY isg_unet_forward_chunks with
  * cudaMemcpyAsync on that call's stream -- no blocking copy, nothing on the legacy stream.
  * Several plans may share one workspace as long as their forward passes are enqueued on the
  * same stream (or otherwise ordered): a forward pass leaves nothing in the workspace that a

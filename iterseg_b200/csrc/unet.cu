@@ -533,7 +533,9 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         return launch_tc(p->tc[i], st);
     };
     ProfScope whole(p, 1, st);
-    if (p->tabs_dirty) {
+    {
+        // every pass uploads its tables: plans may share the workspace, so whatever another plan's
+        // pass left at these addresses is not ours (three small asynchronous copies from pinned memory)
         if (p->tabs_dirty < 0) {
             set_error("isg_unet_forward_chunks: no chunk tables set (isg_unet_plan_set_chunks)");
             return ISG_ERR_ARG;
@@ -852,15 +854,15 @@ extern "C" int isg_unet_plan_set_chunks(isg_unet_plan *plan, const int32_t *star
                         "chunk %d: crop [%d,%d) outside the chunk extent %d", n, lo[a], hi[a], chk[a]);
         }
     }
-    if (plan->tabs_ev_pending) {                           // the previous upload still reads the pinned copy
+    const size_t nb = sizeof(int) * 3 * (size_t)N;
+    if (plan->tabs_dirty >= 0 && memcmp(plan->tabs_host, starts_host, nb) == 0 &&
+        memcmp(plan->tabs_host + 3 * N, crop_lo_host, nb) == 0 &&
+        memcmp(plan->tabs_host + 6 * N, crop_hi_host, nb) == 0)
+        return ISG_OK;                                     // the pinned copy already holds these tables
+    if (plan->tabs_ev_pending) {                           // an enqueued upload still reads the pinned copy
         ISG_CUDA(cudaEventSynchronize(plan->tabs_ev));
         plan->tabs_ev_pending = 0;
     }
-    const size_t nb = sizeof(int) * 3 * (size_t)N;
-    if (plan->tabs_dirty == 0 && memcmp(plan->tabs_host, starts_host, nb) == 0 &&
-        memcmp(plan->tabs_host + 3 * N, crop_lo_host, nb) == 0 &&
-        memcmp(plan->tabs_host + 6 * N, crop_hi_host, nb) == 0)
-        return ISG_OK;                                     // the device already holds these tables
     memcpy(plan->tabs_host, starts_host, nb);
     memcpy(plan->tabs_host + 3 * N, crop_lo_host, nb);
     memcpy(plan->tabs_host + 6 * N, crop_hi_host, nb);

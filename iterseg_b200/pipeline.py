@@ -163,9 +163,11 @@ class SeriesPipeline:
             self.outs = [{'crop': torch.empty(self.shape, dtype=torch.int32, device=self.dev),
                           'host': None, 'ev_post': torch.cuda.Event(), 'ev_d2h': torch.cuda.Event()}
                          for _ in range(self.N_OUT)]
+        # pinned input ring: allocated on first use (page-locking ~35 MB takes milliseconds; a caller
+        # whose frames already sit in pinned float32 memory never needs it)
         self.free_in = queue.Queue()
-        for _ in range(self.N_IN):
-            self.free_in.put(torch.empty(self.shape, dtype=torch.float32).pin_memory())
+        self._n_in_alloc = 0
+        self._in_lock = __import__('threading').Lock()
         self.free_out = queue.Queue()
         for o in range(self.N_OUT):
             self.free_out.put(o)
@@ -181,7 +183,13 @@ class SeriesPipeline:
             t = torch.from_numpy(src)
             if t.is_pinned():
                 return 'direct', t
-        buf = self.free_in.get()
+        buf = None
+        with self._in_lock:
+            if self.free_in.empty() and self._n_in_alloc < self.N_IN:
+                self._n_in_alloc += 1
+                buf = torch.empty(self.shape, dtype=torch.float32).pin_memory()
+        if buf is None:
+            buf = self.free_in.get()
         np.copyto(buf.numpy(), np.asarray(src), casting='unsafe')
         return 'buf', buf
 

@@ -296,7 +296,12 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
                            threshold=config['threshold'])
         return SeriesPipeline(core)
 
+    import time
+    t_start = time.perf_counter()
+    timing = {'frames': 0}
+    LAST_COUNTS['timing'] = timing
     pipe = make_pipe()
+    timing['setup_s'] = time.perf_counter() - t_start
     loaders = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-load')
     writers = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-write')
     SKIP = object()
@@ -345,6 +350,10 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
             t_done = storing.popleft().result()
             if kind == 'affinity':
                 config['unet'].check_overflow()                  # that frame's D2H has completed
+            now = time.perf_counter() - t_start
+            timing.setdefault('first_frame_s', now)
+            timing['last_frame_s'] = now
+            timing['frames'] += 1
             yield t_done
 
     def slow_zero_frame(t):

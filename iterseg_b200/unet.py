@@ -104,7 +104,8 @@ class UNet(nn.Module):
             setattr(self, name, nn.ConvTranspose3d(c, c, kernel_size=k, stride=k, groups=c))
         self._packed = None
         self._plans = {}              # (frame shape, chunk shape, n chunks) -> _Plan, least recently used first
-        self._workspace = None        # ONE activation workspace shared by all plans (they run in stream order)
+        self._workspace = None        # ONE activation workspace shared by all plans
+        self._ws_event = None         # end of the last forward pass that used the workspace
 
     # ---- weights -------------------------------------------------------------------
     @property
@@ -115,6 +116,7 @@ class UNet(nn.Module):
         self._packed = None
         self._plans = {}
         self._workspace = None
+        self._ws_event = None
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -200,10 +202,18 @@ class UNet(nn.Module):
         if out is None:
             out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=frame.device)
         with torch.cuda.device(frame.device):
-            p.workspace.record_stream(torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            # forward passes share the workspace: whatever stream this one is enqueued on, it starts
+            # after the previous one has finished (a device-side wait, nothing blocks on the host)
+            if self._ws_event is not None:
+                cur.wait_event(self._ws_event)
+            p.workspace.record_stream(cur)
             rc = _lib.load().isg_unet_forward_chunks(p.ptr, frame.data_ptr(), out.data_ptr(),
                                                      _lib.stream_ptr())
-        _lib.check(rc, 'isg_unet_forward_chunks')
+            _lib.check(rc, 'isg_unet_forward_chunks')
+            if self._ws_event is None:
+                self._ws_event = torch.cuda.Event()
+            self._ws_event.record(cur)
         return out
 
     def check_overflow(self):

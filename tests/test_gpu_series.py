@@ -121,6 +121,7 @@ def test_plans_share_one_workspace_and_tables_are_per_call(net):
     n_plans = len(net._plans)
     got = torch.zeros_like(want)
     s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())       # vol / got were produced on the default stream
     with torch.cuda.stream(s):                       # a non-default stream, batches of 5 then the rest
         for b in range(0, len(st), 5):
             net.forward_chunks(vol, CHUNK, st[b:b + 5], lo[b:b + 5], hi[b:b + 5], out=got)
@@ -140,6 +141,8 @@ def test_plans_share_one_workspace_and_tables_are_per_call(net):
         sel_a[z + lo[i][0]:z + hi[i][0], y + lo[i][1]:y + hi[i][1], x + lo[i][2]:x + hi[i][2]] = True
     assert torch.equal(a[:, sel_a], want[:, sel_a])
     assert not b_[:, sel_a].any()
+    # back to the whole-frame plan after other plans used (and overwrote) the shared workspace
+    assert torch.equal(predict.predict_frame_device(net, vol, CHUNK, MARGIN), want)
 
 
 def test_capped_flood_workspace_fails_loudly_then_succeeds():

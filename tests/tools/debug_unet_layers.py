@@ -14,12 +14,19 @@ from oracle import unet_ref                   # noqa: E402
 def report(chunk_shape, seed=0, mode=None):
     if mode is not None:
         os.environ['ISG_CONV_BASE_OFFSET'] = str(mode)
-    sd = unet_ref.synth_state_dict(0)
+    if '--structured' in sys.argv:
+        from iterseg_b200 import synth
+        sd = synth.structured_state_dict(0)
+    else:
+        sd = unet_ref.synth_state_dict(0)
     net = U.UNet()
     net.load_state_dict(sd)
     net.cuda()
     rng = np.random.default_rng(seed)
     x = rng.random((1, 1) + chunk_shape, dtype=np.float32)
+    if '--structured' in sys.argv:
+        from iterseg_b200 import synth
+        x = synth.platelet_frame(chunk_shape, seed=1)[None, None]
     ref = {}
     y_ref = unet_ref.unet_forward(torch.from_numpy(x), sd, hook=lambda k, v: ref.__setitem__(k, v.clone()))
     frame = torch.from_numpy(x[0, 0]).cuda()
