@@ -427,12 +427,15 @@ def run_gpu(args, rank, local_rank, world):
     pipe = FramePipeline(net, FRAME, CHUNK, MARGIN)
     offsets = idist.LabelOffsets(rank, world, dev)
 
+    step_events = []
+
     def steps_device(k):
         """k complete frames (all kernels of every frame inside the call): the post stage of
         frame i overlaps the U-Net of frame i+1 on a second stream (iterseg_b200/pipeline.py);
         with world > 1 the per-step all-gather of the label counts and the device-resident
         offset (no host read-back) are part of every step."""
         counts = None
+        step_events.clear()
         pipe.submit(frame)
         for i in range(k):
             if i + 1 < k:
@@ -443,6 +446,9 @@ def run_gpu(args, rank, local_rank, world):
                 _lib.check(lib.isg_crop_labels(lab.data_ptr(), FRAME[0], FRAME[1], FRAME[2], crop.data_ptr(),
                                                off.data_ptr() if off is not None else None,
                                                _lib.stream_ptr()), 'isg_crop_labels')
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(pipe.s_post)
+                step_events.append(ev)
         pipe.drain_to()
         return counts
 
@@ -450,7 +456,7 @@ def run_gpu(args, rank, local_rank, world):
     # through `segmentation.segmentation_loop`, the frame loop behind `segment_data` /
     # `affinity_unet_watershed`; with world > 1 every rank runs its own K frames (weak scaling,
     # like `value`) and the label ids are made global by the per-step all-gather
-    n_e2e = max(4 * args.steps, 16)             # long enough that pipeline fill / drain is amortised
+    n_e2e = max(8 * args.steps, 64)             # long enough that pipeline fill / drain (~1 frame) is amortised
     series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
     out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
     config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False}
@@ -483,6 +489,7 @@ def run_gpu(args, rank, local_rank, world):
     clocks = sampler.stop()
     launches = int(lib.isg_launch_count() - launches0)
     ms_total = e0.elapsed_time(e1)
+    frame_done_ms = [round(e0.elapsed_time(ev), 2) for ev in step_events]     # when each frame's labels were ready
     prof = (ctypes_double_array(5))
     _lib.check(lib.isg_unet_plan_profile_read(plan.ptr, prof), 'profile_read')
     _lib.check(lib.isg_unet_plan_profile(plan.ptr, 0), 'profile')
@@ -590,6 +597,7 @@ def run_gpu(args, rank, local_rank, world):
                        'network': 'synthetic state_dict (structured carriers + dense random weights), '
                                   'fp16 operands / fp32 accumulate (bf16 misses the 1e-2 parity gate)',
                        'l2': 'inputs larger than L2: ~13.8 GB of activations streamed per step',
+                       'frame_done_ms': frame_done_ms,
                        'objects': {'seeds': counts_h[0], 'components': counts_h[2],
                                    'multi_seed_components': counts_h[3]}},
             'e2e': {'value': e2e_value, 'unit': 'voxels/s',

@@ -541,12 +541,15 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             return ISG_ERR_ARG;
         }
         const size_t nb = sizeof(int) * 3 * (size_t)N;
+        static const bool once = getenv("ISG_TABLES_ONCE") != nullptr;      // diagnosis only (unsafe with shared workspaces)
+        if (!(once && p->tabs_dirty == 0)) {
         ISG_CUDA(cudaMemcpyAsync(p->starts, p->tabs_host, nb, cudaMemcpyHostToDevice, st));
         ISG_CUDA(cudaMemcpyAsync(p->crop_lo, p->tabs_host + 3 * N, nb, cudaMemcpyHostToDevice, st));
         ISG_CUDA(cudaMemcpyAsync(p->crop_hi, p->tabs_host + 6 * N, nb, cudaMemcpyHostToDevice, st));
         ISG_CUDA(cudaEventRecord(p->tabs_ev, st));
         p->tabs_ev_pending = 1;
         p->tabs_dirty = 0;
+        }
     }
     const unsigned char *pk = p->packed;
     const PackLayout &L = p->L;

@@ -34,10 +34,10 @@ def chunks_per_batch(unet, chunk_size, n_chunks):
     fewer when the device is short of memory (the workspace the network already holds counts as
     available).  Raises when not even one chunk fits."""
     n = max(1, min(int(n_chunks), MAX_CHUNKS_PER_BATCH))
-    free, _ = torch.cuda.mem_get_info(unet.device)
     held = unet._workspace.numel() if getattr(unet, '_workspace', None) is not None else 0
     if unet_mod.workspace_bytes(n, chunk_size) <= held:
-        return n
+        return n                                       # steady state: no driver query per frame
+    free, _ = torch.cuda.mem_get_info(unet.device)
     budget = held + free // 2
     while n > 1 and unet_mod.workspace_bytes(n, chunk_size) > budget:
         n = (n + 1) // 2
