@@ -143,11 +143,31 @@ def cpu_post(feats):
     return time.perf_counter() - t0, out
 
 
+def cpu_full_frame(vol, sd, threads):
+    """One whole frame on the CPU, nothing extrapolated: all chunks of the make_chunks grid through the fp32
+    U-Net (predict.py:64-126), crop-and-place, then the post-U-Net stage on that feature volume.
+    Returns (seconds, seconds U-Net, seconds post, labels)."""
+    from oracle import chunks as ochunks
+    starts, crops = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
+    t0 = time.perf_counter()
+    _, preds = cpu_unet_chunks(vol, sd, starts, threads)
+    feats = np.zeros((5,) + FRAME, np.float32)
+    for st, cr, pr in zip(starts, crops, preds):
+        sl = tuple(slice(s, s + c) for s, c in zip(st, CHUNK))
+        crs = (slice(None),) + tuple(slice(a, b) for a, b in cr)
+        feats[(slice(None),) + sl][crs] = pr[crs]
+    del preds
+    t_unet = time.perf_counter() - t0
+    t_post, lab = cpu_post(feats)
+    return time.perf_counter() - t0, t_unet, t_post, lab
+
+
 def run_reference(args, rank):
-    """The reference's CPU path on this box's host cores.  One FULL frame is computed once (all 36
-    chunks: an un-extrapolated measurement, and the network-derived feature volume the post stage
-    runs on -- the same kind of features the GPU arm's post stage sees); every timed step then
-    repeats a bounded sample (2 chunks + the whole post stage) and is extrapolated to a frame."""
+    """The reference's CPU path on this box's host cores: every timed step is ONE WHOLE FRAME -- all 36
+    chunks through the fp32 torch-CPU U-Net with every host thread, crop-and-place, the scipy/numpy
+    seeds / mask / components stage and the single-threaded heap flood on that network-derived
+    feature volume.  Nothing is extrapolated unless the run would exceed ~5 minutes (then the
+    remaining steps time 2 of the 36 chunks + the whole post stage and say so)."""
     if rank != 0:
         return 0
     from iterseg_b200 import synth
@@ -156,38 +176,35 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     vol = synth.platelet_frame(FRAME, seed=0)
     sd = synth.structured_state_dict(0)
-    starts, crops = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
+    starts, _ = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
     n_chunks = len(starts)
-    # ---- one whole frame, timed as it is ----
-    t0 = time.perf_counter()
-    t_chunk_full, preds = cpu_unet_chunks(vol, sd, starts, threads)
-    feats = np.zeros((5,) + FRAME, np.float32)
-    for st, cr, pr in zip(starts, crops, preds):
-        sl = tuple(slice(s, s + c) for s, c in zip(st, CHUNK))
-        crs = (slice(None),) + tuple(slice(a, b) for a, b in cr)
-        feats[(slice(None),) + sl][crs] = pr[crs]
-    del preds
-    t_post_full, _ = cpu_post(feats)
-    full_frame_s = time.perf_counter() - t0
-    n_sample = 2
-    pick = [starts[i] for i in np.linspace(0, n_chunks - 1, n_sample).astype(int)]
-    for _ in range(max(args.warmup - 1, 0)):                       # the full frame above was warm-up no. 1
+    pick = [starts[i] for i in np.linspace(0, n_chunks - 1, 2).astype(int)]
+    for _ in range(max(args.warmup, 1)):                           # oneDNN primitives, thread pools, page faults
         cpu_unet_chunks(vol, sd, pick[:1], threads)
-    times, splits = [], []
-    for _ in range(args.steps):
-        t_unet, _ = cpu_unet_chunks(vol, sd, pick, threads)
-        t_post, _ = cpu_post(feats)
-        times.append(t_unet * n_chunks + t_post)
-        splits.append((t_unet, t_post))
+    times, splits, n_full = [], [], 0
+    t_begin = time.perf_counter()
+    for k in range(args.steps):
+        spent = time.perf_counter() - t_begin
+        est = (spent / k) if k else 0.0
+        if k == 0 or spent + est * (args.steps - k) <= 300.0:
+            dt, t_unet, t_post, _ = cpu_full_frame(vol, sd, threads)
+            times.append(dt)
+            splits.append((t_unet / n_chunks, t_post))
+            n_full += 1
+        else:                                                      # bounded sample, extrapolated (flagged)
+            t_unet, _ = cpu_unet_chunks(vol, sd, pick, threads)
+            times.append(t_unet * n_chunks + splits[0][1])
+            splits.append((t_unet, splits[0][1]))
     per_frame = float(np.mean(times))
     nvox = float(np.prod(FRAME))
     value = nvox / per_frame
-    sample = (f'per step {n_sample} of {n_chunks} U-Net chunks timed (fp32 torch CPU, train-mode BN, {threads} threads) '
-              f'and EXTRAPOLATED x{n_chunks}/{n_sample}, plus the full post-U-Net stage (scipy/numpy + C heap flood, one '
-              f'thread like the numba original) on the NETWORK-derived feature volume of the same frame; mean U-Net '
-              f'{np.mean([s[0] for s in splits]):.2f} s/chunk, post {np.mean([s[1] for s in splits]):.2f} s/frame; one '
-              f'whole frame computed without extrapolation took {full_frame_s:.1f} s '
-              f'({nvox / full_frame_s:.0f} voxels/s)')
+    extrapolated = n_full < args.steps
+    sample = (f'{n_full} of {args.steps} steps are whole frames: all {n_chunks} U-Net chunks (fp32 torch CPU, train-mode BN, '
+              f'{threads} threads), crop-and-place and the full post-U-Net stage (scipy/numpy + C heap flood, one thread '
+              f'like the numba original) on the NETWORK-derived feature volume; mean U-Net '
+              f'{np.mean([s[0] for s in splits]):.2f} s/chunk, post {np.mean([s[1] for s in splits]):.2f} s/frame'
+              + ('; the other steps time 2 chunks and are extrapolated (time budget)' if extrapolated else
+                 '; nothing extrapolated'))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'voxels/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -195,8 +212,8 @@ def run_reference(args, rank):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'frame': list(FRAME), 'chunk': list(CHUNK), 'margin': list(MARGIN)},
         'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                         'sample': sample, 'extrapolated': True,
-                         'full_frame_s': full_frame_s, 'full_frame_voxels_per_s': nvox / full_frame_s},
+                         'sample': sample, 'extrapolated': extrapolated,
+                         'step_s': [round(t, 2) for t in times]},
         'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -259,7 +276,32 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
         assert done == own, (done[:4], own[:4])
         return float(dt.item())
 
-    # (a) every rank's frames into its own pinned (T_own) block of an in-memory array: no file I/O
+    # (a) every rank's frames into its own pinned block of an in-memory array: no file I/O
+    class OwnFrames:
+        """(n_frames, Z, Y, X) int32 label array of which only this rank's frames exist (pinned)."""
+        def __init__(self):
+            self.shape, self.ndim, self.dtype = (n_frames,) + FRAME, 4, np.dtype(np.int32)
+            self.block = torch.zeros((len(own),) + FRAME, dtype=torch.int32).pin_memory()
+            self.np = self.block.numpy()
+            self.at = {t: i for i, t in enumerate(own)}
+
+        def __getitem__(self, t):
+            return self.np[self.at[int(t)]]
+
+        def __setitem__(self, key, value):
+            t = key[0] if isinstance(key, tuple) else key
+            self.np[self.at[int(t)]][...] = value
+
+    if world > 1:
+        out = OwnFrames()
+        dt = timed(out)
+        tm = dict(segmentation.LAST_COUNTS.get('timing', {}))
+        rec['in_memory'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3,
+                            'first_frame_s': tm.get('first_frame_s'),
+                            'steady_ms_per_frame_per_rank': ((tm['last_frame_s'] - tm['first_frame_s']) /
+                                                             max(tm['frames'] - 1, 1) * 1e3 if tm.get('frames', 0) > 1 else None),
+                            'note': 'every rank keeps its frames in its own pinned block (no file I/O)'}
+        del out
     mem = torch.zeros((n_frames,) + FRAME, dtype=torch.int32).pin_memory() if world == 1 else None
     if mem is not None:
         dt = timed(mem.numpy())
@@ -326,11 +368,22 @@ def slab_record(net, rank, world, dev, barrier, shape=(256, 2048, 2048), halo=16
     out_host = torch.empty((me.z1 - me.z0,) + tuple(shape[1:]), dtype=torch.int32).pin_memory()
     n_labels = None
     times = []
+    halo_retries = []
     for it in range(2):                 # warm-up (plans, workspaces, NCCL channels) + timed
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        own, (z0, z1), n_labels = islab.segment_volume_slabs(vol, net, CHUNK, MARGIN, halo=halo)
+        while True:
+            try:
+                own, (z0, z1), n_labels = islab.segment_volume_slabs(vol, net, CHUNK, MARGIN, halo=halo)
+                break
+            except islab.HaloTooSmall:                             # raised on every rank together
+                pass
+            halo += 8                                              # the guard refused: never an approximation
+            halo_retries.append(halo)
+            if halo > 48:
+                raise RuntimeError('objects longer than 48 planes: not a slab workload')
+            e0.record()
         out_host.copy_(own, non_blocking=True)
         e1.record()
         torch.cuda.synchronize()
@@ -340,7 +393,7 @@ def slab_record(net, rank, world, dev, barrier, shape=(256, 2048, 2048), halo=16
     ms = times[-1]
     nvox = float(np.prod(shape))
     n_chunks = int(sum(len(s.chunks) for s in slabs))
-    rec = {'volume': list(shape), 'chunks': n_chunks, 'halo_planes': halo, 'slabs': [[s.z0, s.z1] for s in slabs],
+    rec = {'volume': list(shape), 'chunks': n_chunks, 'halo_planes': halo, 'halo_raised_to': halo_retries, 'slabs': [[s.z0, s.z1] for s in slabs],
            'ms': ms, 'warmup_ms': times[0], 'voxels_per_s': nvox / (ms * 1e-3),
            'chunks_per_s_per_gpu': n_chunks / world / (ms * 1e-3), 'labels': int(n_labels),
            'synth_s': round(t_gen, 2),
@@ -390,6 +443,12 @@ def slab_record(net, rank, world, dev, barrier, shape=(256, 2048, 2048), halo=16
     else:
         dist.send(own_dev, dst=0)
     return rec
+
+
+def _agreement(a, b):
+    from oracle import metrics
+    return {'variation_of_information': float(sum(metrics.variation_of_information(a, b))),
+            'matched_f1': float(metrics.matched_f1(a, b, 0.5)), 'objects': [int(a.max()), int(b.max())]}
 
 
 def run_gpu(args, rank, local_rank, world):
@@ -641,20 +700,21 @@ def run_gpu(args, rank, local_rank, world):
             line['slab'] = slab_rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            from oracle import chunks as ochunks, flood as oflood
+            from oracle import flood as oflood
             oflood.build()
-            starts, _ = ochunks.make_chunks(FRAME, CHUNK, MARGIN)
-            pick = [starts[i] for i in np.linspace(0, len(starts) - 1, 3).astype(int)]
-            t_unet, _ = cpu_unet_chunks(vol_np, sd, pick, threads)
-            t_post, lab_cpu = cpu_post(feats_host)
-            per_frame = t_unet * len(starts) + t_post
+            cpu_unet_chunks(vol_np, sd, [(0, 0, 0)], threads)             # warm-up: oneDNN primitives, thread pool
+            dt, t_unet, t_post, lab_cpu = cpu_full_frame(vol_np, sd, threads)
+            t_post_gpu_feats, lab_cpu2 = cpu_post(feats_host)
             line['cpu_baseline'] = {
-                'value': nvox / per_frame, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port', 'extrapolated': True,
-                'sample': (f'3 of {len(starts)} U-Net chunks timed on {threads} threads ({t_unet:.2f} s/chunk, fp32 '
-                           f'torch CPU, train-mode BN) extrapolated to {len(starts)}; full post-U-Net stage '
-                           f'({t_post:.2f} s, single thread) on the SAME network-derived feature volume the GPU '
-                           f'post stage ran on'),
-                'post_labels_equal_gpu': bool(np.array_equal(lab_cpu, labels.cpu().numpy().view(np.uint32)))}
+                'value': nvox / dt, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port', 'extrapolated': False,
+                'sample': (f'ONE WHOLE FRAME of the same workload, nothing extrapolated: all 36 U-Net chunks on {threads} '
+                           f'threads ({t_unet:.2f} s, fp32 torch CPU, train-mode BN), crop-and-place, the full '
+                           f'post-U-Net stage ({t_post:.2f} s, single thread) on that network-derived feature volume'),
+                's': dt,
+                # the CPU post stage on the feature volume the GPU U-Net produced == the GPU labels, bit for bit
+                'post_on_gpu_features_equals_gpu_labels': bool(np.array_equal(lab_cpu2, labels.cpu().numpy().view(np.uint32))),
+                # end-to-end agreement of the two arms on this frame (gate: VI <= 0.01, F1 >= 0.99)
+                'labels_vs_gpu': _agreement(lab_cpu[1:-1, 1:-1, 1:-1], labels.cpu().numpy().view(np.uint32)[1:-1, 1:-1, 1:-1])}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -780,7 +840,7 @@ def main():
     ap.add_argument('--no-slab-check', action='store_true',
                     help='skip the single-device run the slab labels are compared with')
     ap.add_argument('--slab-shape', type=int, nargs=3, default=[256, 2048, 2048])
-    ap.add_argument('--slab-halo', type=int, default=16)
+    ap.add_argument('--slab-halo', type=int, default=24)
     ap.add_argument('--segmenter', default='affinity', choices=['affinity', 'dog'],
                     help="'dog': the DoG blob watershed (BASELINE.json configs[4]) instead of the headline path")
     args = ap.parse_args()

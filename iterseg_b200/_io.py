@@ -122,6 +122,32 @@ class LabelArray:
                 os.ftruncate(fd, nbytes)                 # extending keeps what other writers stored
         finally:
             os.close(fd)
+        # leading axes that are indexed, trailing axes that are taken whole: every index tuple of the
+        # leading part is ONE contiguous byte run of the file -> positional writes (pwrite), which
+        # fill the page cache in bulk (a frame of a tzyx t-chunk is a single 17 MB run); anything
+        # else goes through a shared mapping
+        k = self.ndim
+        while k > 0 and src[k - 1].start == 0 and src[k - 1].stop == self.chunks[k - 1]:
+            k -= 1
+        k = min(k + 1, self.ndim)                       # the innermost indexed axis is contiguous too
+        lead = [range(sl.start, sl.stop) for sl in src[:k - 1]]
+        n_runs = int(np.prod([len(r) for r in lead])) if lead else 1
+        if n_runs <= 64:
+            import itertools
+            blk = np.ascontiguousarray(block, dtype=self.dtype.newbyteorder('<'))
+            strides = [int(np.prod(self.chunks[i + 1:])) * self.dtype.itemsize for i in range(self.ndim)]
+            fd = os.open(fn, os.O_RDWR)
+            try:
+                for idx_lead in itertools.product(*lead):
+                    off = sum(i * st for i, st in zip(idx_lead, strides)) + src[k - 1].start * strides[k - 1]
+                    sub = blk[tuple(i - sl.start for i, sl in zip(idx_lead, src[:k - 1]))]
+                    view = memoryview(np.ascontiguousarray(sub)).cast('B')
+                    done = 0
+                    while done < len(view):
+                        done += os.pwrite(fd, view[done:], off + done)
+            finally:
+                os.close(fd)
+            return
         mm = np.memmap(fn, dtype=self.dtype.newbyteorder('<'), mode='r+', shape=self.chunks)
         mm[src] = block
         mm.flush()

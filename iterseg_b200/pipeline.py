@@ -141,7 +141,7 @@ class SeriesPipeline:
     `core` is a FramePipeline (affinity U-Net watershed) or a DogCore."""
 
     N_IN = 4        # pinned input buffers / device frame buffers
-    N_OUT = 3       # device crop buffers / pinned output buffers
+    N_OUT = 4       # device crop buffers / pinned output buffers (= frames the writer threads may hold)
 
     def __init__(self, core, normalise=True):
         import queue

@@ -303,7 +303,7 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
     pipe = make_pipe()
     timing['setup_s'] = time.perf_counter() - t_start
     loaders = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-load')
-    writers = cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='isg-write')
+    writers = cf.ThreadPoolExecutor(max_workers=4, thread_name_prefix='isg-write')
     SKIP = object()
 
     def load(t):
@@ -394,7 +394,7 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
                 continue
             if running:
                 collect_one()
-            yield from finished(2)
+            yield from finished(3)
         while running:
             collect_one()
         if offsets is not None:                                  # ranks with fewer frames keep the lock-step

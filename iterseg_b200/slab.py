@@ -265,9 +265,10 @@ class SlabWorker:
             seeds, counts, mask, _ = watershed.segment_features_device(
                 self.feats_ext, self.labels_ext, aff, cent, tch, **kw)
         c = counts.cpu().numpy()
-        if c[4]:
-            raise HaloTooSmall(f'rank {self.rank}: an object that reaches planes [{self.slab.z0},{self.slab.z1}) '
-                               f'is cut by the halo of {self.halo} planes; re-run with a larger halo')
+        # an object that reaches the own planes is cut by an open face of the extended slab: the caller
+        # combines this flag over the ranks (MAX) and calls `check_halo` -- all ranks raise together,
+        # none is left waiting in a collective
+        self.halo_violation = int(c[4])
         self.n_local = int(c[0])
         k = keys[:self.n_local]
         # local key = (~ord(value) << 32) | local unpadded flat index  ->  global flat index
@@ -277,6 +278,12 @@ class SlabWorker:
         own = (zl >= self.own0) & (zl < self.own1)
         self.mask_ext = mask
         return self.keys_global[own].contiguous()
+
+    def check_halo(self, any_violation):
+        if any_violation:
+            raise HaloTooSmall(f'an object that reaches the own planes of a rank is cut by the halo of {self.halo} '
+                               f'planes (rank {self.rank}: {"yes" if self.halo_violation else "no"}); re-run with a '
+                               f'larger halo')
 
     # ---- phase 6: global label ids -----------------------------------------------------------
     def relabel(self, global_sorted_keys):
@@ -338,6 +345,9 @@ def segment_volume_emulated(volume, net, chunk_size, margin, world, halo=24, fea
     hist = torch.stack([w.stats1(gmin, gmax_s) for w in ws]).sum(0)
     thr = SlabWorker.otsu(hist, gmin, gmax_s)
     keys = torch.cat([w.segment(thr, chan) for w in ws])
+    bad = any(w.halo_violation for w in ws)
+    for w in ws:
+        w.check_halo(bad)
     gsorted = sort_keys(keys)
     out = np.zeros(shape, dtype=np.uint32)
     for w in ws:
@@ -391,6 +401,9 @@ def segment_volume_slabs(volume, net, chunk_size, margin, halo=24, group=None, f
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     thr = SlabWorker.otsu(hist, mn, mx)
     own_keys = w.segment(thr, chan)
+    bad = torch.tensor([w.halo_violation], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+    w.check_halo(int(bad.item()))
     # seam label merge: all-gather the (padded) key lists, sort, relabel
     cnt = torch.tensor([own_keys.numel()], dtype=torch.int64, device=dev)
     cnts = [torch.zeros_like(cnt) for _ in range(world)]
