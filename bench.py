@@ -244,7 +244,7 @@ def conv_traffic():
     return float(d['dram_bytes_per_launch']), 'ncu --set full, ' + str(d.get('source', 'profiles/'))
 
 
-def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
+def series_record(net, rank, world, dev, barrier, save_root, n_frames=192, segmenter='affinity'):
     """BASELINE.json configs[2]: ONE n_frames-frame tzyx series through the public frame loop
     (`segmentation.segmentation_loop`, what `segment_data` runs), frames sharded t = rank (mod
     world) when world > 1, global label ids from the per-step NCCL all-gather, every rank writing
@@ -258,16 +258,27 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
     data = synth.JitteredSeries(n_frames, FRAME, n_base=4, own=own, pin=True)
     t_gen = time.perf_counter() - t0
     nvox = float(np.prod(FRAME)) * n_frames
-    cfg = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'global_label_offsets': True}
-    rec = {'frames': n_frames, 'frames_per_rank': len(own), 'scaling': 'strong',
-           'api': 'segmentation.segmentation_loop (frames t = rank mod world, global label offsets by an NCCL '
-                  'all-gather per step, device-resident prefix)', 'synth_s': round(t_gen, 2)}
+    if segmenter == 'affinity':
+        fn = segmentation.affinity_watershed_for_chunks
+        cfg = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'global_label_offsets': True}
+        api = ('segmentation.segmentation_loop (frames t = rank mod world, global label offsets by an NCCL '
+               'all-gather per step, device-resident prefix)')
+    else:
+        fn = segmentation.dog_blob_watershed_for_chunks
+        cfg = {'min_sigma': 1, 'max_sigma': 1.5, 'threshold': 0.02}
+        api = 'segmentation.segmentation_loop with the DoG blob segmenter (frames t = rank mod world, labels per frame)'
+    rec = {'frames': n_frames, 'frames_per_rank': len(own), 'scaling': 'strong', 'api': api, 'synth_s': round(t_gen, 2)}
+
+    # warm-up through the same API (one-off costs: lazily loaded kernels, NCCL channels, pinned rings)
+    wu = synth.JitteredSeries(2 * world, FRAME, n_base=1, own=idist.shard_frames(2 * world, rank, world), pin=True)
+    wu_out = _io.zeros((2 * world,) + FRAME, CHUNK, np.int32)
+    list(segmentation.segmentation_loop(None, wu, CHUNK, MARGIN, wu_out, fn, dict(cfg)))
+    del wu, wu_out
 
     def timed(out):
         barrier()
         t0 = time.perf_counter()
-        done = list(segmentation.segmentation_loop(None, data, CHUNK, MARGIN, out,
-                                                   segmentation.affinity_watershed_for_chunks, cfg))
+        done = list(segmentation.segmentation_loop(None, data, CHUNK, MARGIN, out, fn, cfg))
         torch.cuda.synchronize()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -310,9 +321,10 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
                             'setup_s': tm.get('setup_s'), 'first_frame_s': tm.get('first_frame_s'),
                             'steady_ms_per_frame': ((tm['last_frame_s'] - tm['first_frame_s']) / max(tm['frames'] - 1, 1) * 1e3
                                                     if tm.get('frames', 0) > 1 else None)}
-        total = int(segmentation.LAST_COUNTS['global_total'].item())
-        rec['labels_total'] = total
-        rec['labels_global_ok'] = bool(int(mem[-1].max()) == total and int(mem[0].max()) < int(mem[-1].max()))
+        if segmenter == 'affinity':
+            total = int(segmentation.LAST_COUNTS['global_total'].item())
+            rec['labels_total'] = total
+            rec['labels_global_ok'] = bool(int(mem[-1].max()) == total and int(mem[0].max()) < int(mem[-1].max()))
         del mem
     # (b) ONE OME-zarr label store shared by all ranks (save_dir of segment_data; chunks = chunk_size
     #     on tzyx data = 10-frame t-chunks, segmentation.py:776-782)
@@ -325,7 +337,7 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
     if rank != 0:
         arr = _io.open_zarr(os.path.join(store, '0'), shape=data.shape, chunks=CHUNK, dtype=np.int32)
     dt = timed(arr)
-    total = int(segmentation.LAST_COUNTS['global_total'].item())
+    total = int(segmentation.LAST_COUNTS['global_total'].item()) if segmenter == 'affinity' else None
     tm = dict(segmentation.LAST_COUNTS.get('timing', {}))
     rec['zarr'] = {'s': dt, 'voxels_per_s': nvox / dt, 'ms_per_frame': dt / n_frames * 1e3,
                    'setup_s': tm.get('setup_s'), 'first_frame_s': tm.get('first_frame_s'),
@@ -337,7 +349,8 @@ def series_record(net, rank, world, dev, barrier, save_root, n_frames=192):
         # frames of different ranks that share one t-chunk file, read back: non-empty, ids ascending
         mx = [int(np.asarray(arr[t]).max()) for t in (0, 1, 9, n_frames - 1)]
         rec['zarr_readback_max_label'] = mx
-        rec['zarr_ok'] = bool(mx[0] > 0 and mx[0] < mx[1] < mx[2] < mx[3] and mx[3] == total)
+        rec['zarr_ok'] = (bool(mx[0] > 0 and mx[0] < mx[1] < mx[2] < mx[3] and mx[3] == total) if total is not None
+                          else bool(min(mx) > 0))
     return rec
 
 
@@ -784,6 +797,27 @@ def run_dog(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    series_rec = None
+    if not args.no_series:
+        import tempfile
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        save_root = tempfile.mkdtemp(prefix='isg_bench_') if rank == 0 else None
+        if world > 1:
+            box = [save_root]
+            dist.broadcast_object_list(box, src=0)
+            save_root = box[0]
+        try:
+            series_rec = series_record(None, rank, world, dev, barrier, save_root, n_frames=args.series_frames,
+                                       segmenter='dog')
+        except Exception as e:                                    # noqa: BLE001
+            series_rec = {'error': repr(e)[:300]}
+        if rank == 0:
+            import shutil
+            shutil.rmtree(save_root, ignore_errors=True)
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm = float(peaks.get('hbm_gbs_sustained', peaks.get('hbm_gbs', 6650.0)))
@@ -806,6 +840,8 @@ def run_dog(args, rank, local_rank, world):
                          'kernel': 'whole DoG stage (12 separable Gaussian passes, peaks, EDT, flood)',
                          'peak_source': f'{peak_kind} hbm_gbs; 8 B per voxel compulsory (f32 in, i32 out)'},
         }
+        if series_rec is not None:
+            line['series'] = series_rec
         if world == 1 and not args.no_cpu_baseline:
             from oracle import dog
             out = np.zeros(shape_p, np.int32)

@@ -277,6 +277,9 @@ double isg_unet_plan_flops(const isg_unet_plan *plan);
  *           algorithmic FLOPs of the tcgen05 convolutions of ONE forward}. */
 int isg_unet_plan_profile(isg_unet_plan *plan, int enable);
 int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out);
+/* per-launch times (ms) of the recorded forward passes in launch order, 35 launches per forward;
+ * kind_out (nullable): 0 = TMA-fed tcgen05 convolution, 2 = any other kernel.  Returns the count. */
+int isg_unet_plan_profile_launches(isg_unet_plan *plan, double *ms_out, int *kind_out, int cap);
 
 /* ---- label bookkeeping for frame-sharded time series ------------------------
  * labels[i] += offset for every non-zero label (global label ids across frames:

@@ -208,6 +208,24 @@ static void choose_tile(int H, int W, int rb, int &P, int &Ht) {
     }
 }
 
+// Band-flat tiling (ConvGeom::flat): pitch P = band width + 2, R = the padded rows a 128-position
+// tile plus its 2P + 2 tap reach can touch, fewest tiles first, then the smallest slot.
+static bool choose_flat(int H, int W, int rb, long max_slot, int &P, int &R, long &tiles) {
+    long best_t = -1, best_s = 0;
+    for (int p = 10; p <= 256; ++p) {
+        const int wb = p - 2;
+        const int r = (p - 1 + 128 + 2 * p + 2 + p - 1) / p;
+        const long slot = (((long)r * p * rb) + 1023) & ~1023L;
+        if (slot > max_slot || r > 256) continue;
+        const long t = (long)((W + wb - 1) / wb) * (((long)H * p + 127) / 128);
+        if (best_t < 0 || t < best_t || (t == best_t && slot < best_s)) {
+            best_t = t; best_s = slot; P = p; R = r;
+        }
+    }
+    tiles = best_t;
+    return best_t > 0;
+}
+
 static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
     const int N = p->N;
     auto vox = [&](int l) { return (size_t)N * p->D[l] * p->H[l] * p->W[l]; };
@@ -330,54 +348,99 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     // Per candidate: T output planes per group = as many accumulators as the set holds, balanced
     // over the z extent; then the weight ring: everything resident if it fits, else G taps per
     // stage (a stage <= 36 KB) and as many stages as fit (>= 2).
-    const bool want_fold = g.cout <= 64 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
-    bool placed = false;
+    // fold pays for Cout = 32 only: with Cout = 64 the plain kernel (N = 64 at ~48 clk per MMA, a plain
+    // epilogue) beats the fold's N = 192 with its three TMEM reads and 64 shuffles per 32 columns
+    // (c1.conv0: 1.15 -> 0.74 ms, profiles/r02_notes.md)
+    const bool want_fold = g.cout <= 32 && g.W >= 100 && getenv("ISG_CONV_NOFOLD") == nullptr;
+    // band-flat tiling for the plain layers (ISG_CONV_NOFLAT=1: the rectangular patches of round 1);
+    // ISG_CONV_FLAT_KB bounds the plane slot (default 32 KB)
+    const bool want_flat = getenv("ISG_CONV_NOFLAT") == nullptr;
+    const long flat_kb = getenv("ISG_CONV_FLAT_KB") ? atol(getenv("ISG_CONV_FLAT_KB")) : 32;
     // pass 0: weights resident -> tile-major issue order, where ONE set of T accumulators already
     //         works as a ring (tile t's epilogue overlaps tiles t+1..), so T can use all of TMEM;
     // pass 1: streamed weights -> weight-stationary order, two accumulator sets.
-    for (int pass = 0; pass < 2 && !placed; ++pass) {
-        for (int cand = want_fold ? 0 : 1; cand < 2 && !placed; ++cand) {
-            const bool fold = cand == 0;
-            const int acc = fold ? 3 * g.cout : g.cout;
-            const int nsets = pass == 0 ? 1 : ((!fold && g.cout >= 256) ? 1 : 2);
-            int tmax = (512 / nsets) / acc;
-            if (tmax < 1) continue;
-            if (fold) { g.P = 32; g.Ht = 4; }
-            else choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
-            g.plane_rows = (g.Ht + 2) * g.P;
-            g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
-            if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
-            if (tmax > g.D) tmax = g.D;
-            for (; tmax >= 1 && !placed; --tmax) {
-                const int ngr = (g.D + tmax - 1) / tmax;
-                const int T = (g.D + ngr - 1) / ngr;
-                const long avail = budget - (long)(T + 2) * g.plane_bytes;
-                if (avail <= 0) continue;
-                if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
-                    g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
-                    g.b_resident = 1;
-                    placed = true;
-                } else if (pass == 1 && (!fold || T >= 2)) {
-                    for (int G : {9, 3, 1}) {
-                        if (fold && G == 1) continue;
-                        const long sb = (long)G * tap_bytes;
-                        if (sb > 36 * 1024 && G > 1) continue;
-                        long nb = avail / sb;
-                        if (nb < 2) continue;
-                        if (nb > 6) nb = 6;
-                        g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
-                        g.b_resident = 0;
-                        placed = true;
-                        break;
+    auto place = [&](bool allow_flat, long slot_cap) -> bool {
+        bool placed = false;
+        for (int pass = 0; pass < 2 && !placed; ++pass) {
+            for (int cand = want_fold ? 0 : 1; cand < 2 && !placed; ++cand) {
+                const bool fold = cand == 0;
+                const int acc = fold ? 3 * g.cout : g.cout;
+                const int nsets = pass == 0 ? 1 : ((!fold && g.cout >= 256) ? 1 : 2);
+                int tmax = (512 / nsets) / acc;
+                if (tmax < 1) continue;
+                g.flat = 0;
+                if (fold) { g.P = 32; g.Ht = 4; }
+                else {
+                    choose_tile(g.H, g.W, cblk * 2, g.P, g.Ht);
+                    int fp = 0, fr = 0;
+                    long ft = 0;
+                    const long rect_tiles = (long)((g.W + g.P - 3) / (g.P - 2)) * ((g.H + g.Ht - 1) / g.Ht);
+                    if (allow_flat && choose_flat(g.H, g.W, cblk * 2, slot_cap, fp, fr, ft) && ft < rect_tiles) {
+                        g.flat = 1;
+                        g.P = fp;
+                        g.Ht = fr - 2;                       // the TMA box holds Ht + 2 = R padded rows
                     }
                 }
-                if (placed) {
-                    g.nsets = nsets;
-                    g.acc_cols = acc;
-                    t.fold = fold ? 1 : 0;
+                g.plane_rows = (g.Ht + 2) * g.P;
+                g.plane_bytes = (g.plane_rows * cblk * 2 + 1023) & ~1023;
+                if (tmax > CONV_MAX_T) tmax = CONV_MAX_T;
+                if (tmax > g.D) tmax = g.D;
+                for (; tmax >= 1 && !placed; --tmax) {
+                    const int ngr = (g.D + tmax - 1) / tmax;
+                    const int T = (g.D + ngr - 1) / ngr;
+                    const long avail = budget - (long)(T + 2) * g.plane_bytes;
+                    if (avail <= 0) continue;
+                    if ((long)nkb * 27 * tap_bytes <= avail && nkb * 3 <= CONV_MAX_B_STAGES) {
+                        g.T = T; g.taps_per_b = 9; g.b_stage_bytes = 9 * tap_bytes; g.n_b_stages = nkb * 3;
+                        g.b_resident = 1;
+                        placed = true;
+                    } else if (pass == 1 && (!fold || T >= 2)) {
+                        for (int G : {9, 3, 1}) {
+                            if (fold && G == 1) continue;
+                            const long sb = (long)G * tap_bytes;
+                            if (sb > 36 * 1024 && G > 1) continue;
+                            long nb = avail / sb;
+                            if (nb < 2) continue;
+                            if (nb > 6) nb = 6;
+                            g.T = T; g.taps_per_b = G; g.b_stage_bytes = (int)sb; g.n_b_stages = (int)nb;
+                            g.b_resident = 0;
+                            placed = true;
+                            break;
+                        }
+                    }
+                    if (placed) {
+                        g.nsets = nsets;
+                        g.acc_cols = acc;
+                        t.fold = fold ? 1 : 0;
+                    }
+                    if (pass == 0 && !placed && T <= 2) break;      // resident only pays with a few tiles per group
                 }
-                if (pass == 0 && !placed && T <= 2) break;      // resident only pays with a few tiles per group
             }
+        }
+        return placed;
+    };
+    // The rectangular placement is the reference point; a band-flat tiling is taken when it needs
+    // fewer tiles AND leaves the pipeline as it was (same planes per group, accumulator sets, weight
+    // ring granularity, at most one weight stage fewer): measured on B200, flat tiles are worth
+    // 7-11 % on the T = 2 layers, while a layer whose bigger plane slots cost it planes per group or
+    // weight stages loses more than the tiles gain (c1.conv1 1.46 -> 1.98 ms, c6_0.conv0 1.38 -> 1.83 ms).
+    bool placed = place(false, 0);
+    if (placed && want_flat && !t.fold) {
+        const ConvGeom rect = g;
+        const int rect_fold = t.fold;
+        bool took = false;
+        for (long kb : {flat_kb, 28L, 24L, 20L}) {
+            if (kb > flat_kb) continue;
+            if (place(true, kb * 1024) && g.flat && !t.fold && g.T == rect.T && g.nsets == rect.nsets &&
+                g.b_resident == rect.b_resident && g.taps_per_b == rect.taps_per_b &&
+                g.n_b_stages >= rect.n_b_stages - 1) {
+                took = true;
+                break;
+            }
+        }
+        if (!took) {
+            g = rect;
+            t.fold = rect_fold;
         }
     }
     if (!placed) {
@@ -386,7 +449,11 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     }
     g.Wt = g.P - 2;
     g.tiles_w = (g.W + g.Wt - 1) / g.Wt;
-    g.tiles_h = (g.H + g.Ht - 1) / g.Ht;
+    g.tiles_h = g.flat ? (g.H * g.P + 127) / 128 : (g.H + g.Ht - 1) / g.Ht;
+    if (getenv("ISG_CONV_VERBOSE"))
+        fprintf(stderr, "conv %-11s %s P=%d Ht=%d tiles/plane=%d T=%d sets=%d resident=%d G=%d stages=%d slot=%d B\n",
+                CONVS[i].name, t.fold ? "fold" : (g.flat ? "flat" : "rect"), g.P, g.Ht, g.tiles_w * g.tiles_h, g.T,
+                g.nsets, g.b_resident, g.taps_per_b, g.n_b_stages, g.plane_bytes);
     g.dgroups = (g.D + g.T - 1) / g.T;
     g.n_groups = g.N * g.dgroups * g.tiles_h * g.tiles_w;
     g.out_mode = out_mode;
@@ -560,6 +627,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     ISG_CUDA(cudaMemsetAsync(p->stats_all, 0, p->stats_bytes, st));
     // ---- c0.conv0 (1 -> 32, im2col on tensor cores, straight from the frame) ----
     {
+        ProfScope ps(p, 2, st);
         ThinArgs a{};
         a.src = frame; a.starts = p->starts; a.Y = p->Y; a.X = p->X;
         a.wgt = reinterpret_cast<const float *>(pk + L.w[0]);
@@ -578,13 +646,17 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             if (rc) return rc;
             if (stop == i0) return ISG_OK;
         }
-        bn_relu_kernel<<<egrid(vox(l) * CH[l] / 8, N), 256, 0, st>>>(p->raw[l], p->act[l], p->stats[i0],
-                                                                     G(i0), B(i0), E(i0), CH[l], vox(l));
-        ISG_LAUNCHED();
+        {
+            ProfScope ps(p, 2, st);
+            bn_relu_kernel<<<egrid(vox(l) * CH[l] / 8, N), 256, 0, st>>>(p->raw[l], p->act[l], p->stats[i0],
+                                                                         G(i0), B(i0), E(i0), CH[l], vox(l));
+            ISG_LAUNCHED();
+        }
         int rc = run_tc(i1);
         if (rc) return rc;
         if (stop == i1) return ISG_OK;
         if (l < 4) {
+            ProfScope ps(p, 2, st);
             const size_t work = vox(l + 1) * CH[l] / 8;
             if (l == 3)
                 bn_relu_pool_kernel<2><<<egrid(work, N), 256, 0, st>>>(
@@ -606,6 +678,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         const float *ub = reinterpret_cast<const float *>(pk + L.up_b[u]);
         const size_t work = vox(lc) * C / 8;
         const int off = u == 3 ? 1 : 0;
+        ProfScope *ups = new ProfScope(p, 2, st);
         if (u == 0)
             bn_relu_up_kernel<2><<<egrid(work, N), 256, (size_t)(3 + 8) * C * sizeof(float), st>>>(
                 p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), E(src_conv), uw, ub, C, p->D[lc],
@@ -614,6 +687,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
             bn_relu_up_kernel<1><<<egrid(work, N), 256, (size_t)(3 + 4) * C * sizeof(float), st>>>(
                 p->raw[lc], p->up[lf], p->stats[src_conv], G(src_conv), B(src_conv), E(src_conv), uw, ub, C, p->D[lc],
                 p->H[lc], p->W[lc], p->D[lf], p->H[lf], p->W[lf], off);
+        delete ups;
         ISG_LAUNCHED();
         const int i0 = 10 + 2 * u, i1 = i0 + 1;
         int rc = run_tc(i0);                        // reads [up, skip] of level lf
@@ -621,9 +695,12 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         if (stop == i0) return ISG_OK;
         if (u < 3) {
             const int Cm = CONVS[i0].cout;
-            bn_relu_kernel<<<egrid(vox(lf) * Cm / 8, N), 256, 0, st>>>(p->raw[lf], p->act[lf], p->stats[i0],
-                                                                       G(i0), B(i0), E(i0), Cm, vox(lf));
-            ISG_LAUNCHED();
+            {
+                ProfScope ps(p, 2, st);
+                bn_relu_kernel<<<egrid(vox(lf) * Cm / 8, N), 256, 0, st>>>(p->raw[lf], p->act[lf], p->stats[i0],
+                                                                           G(i0), B(i0), E(i0), Cm, vox(lf));
+                ISG_LAUNCHED();
+            }
             rc = run_tc(i1);
             if (rc) return rc;
             if (stop == i1) return ISG_OK;
@@ -631,6 +708,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     }
     // ---- c8_0.conv1 (5 -> 5) + BN + sigmoid + placement ----
     {
+        ProfScope ps(p, 2, st);
         ZoutArgs a{};
         ZringGeom &z = a.g;
         z.N = N; z.D = p->D[0]; z.H = p->H[0]; z.W = p->W[0];
@@ -650,10 +728,13 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     if (feats == nullptr) return ISG_OK;
     ISG_CUDA(cudaMemcpyFromSymbolAsync(p->overflow_host, g_unet_overflow, sizeof(unsigned int), 0,
                                        cudaMemcpyDeviceToHost, st));
-    place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), E(17), p->starts,
-                                                   p->crop_lo, p->crop_hi, feats, p->Z, p->Y, p->X,
-                                                   p->D[0], p->H[0], p->W[0]);
-    ISG_LAUNCHED();
+    {
+        ProfScope ps(p, 2, st);
+        place_kernel<<<egrid(vox(0), N), 256, 0, st>>>(p->raw9, p->stats[17], G(17), B(17), E(17), p->starts,
+                                                       p->crop_lo, p->crop_hi, feats, p->Z, p->Y, p->X,
+                                                       p->D[0], p->H[0], p->W[0]);
+        ISG_LAUNCHED();
+    }
     return ISG_OK;
 }
 
@@ -892,10 +973,27 @@ extern "C" int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out) {
         float ms = 0;
         ISG_CUDA(cudaEventElapsedTime(&ms, plan->ev[s], plan->ev[s + 1]));
         if (plan->ev_kind[s / 2] == 0) { tc_ms += ms; ++n_tc; }
-        else { all_ms += ms; ++n_fw; }
+        else if (plan->ev_kind[s / 2] == 1) { all_ms += ms; ++n_fw; }
     }
     out[0] = tc_ms; out[1] = n_tc; out[2] = all_ms; out[3] = n_fw; out[4] = plan->tc_flops;
     return ISG_OK;
+}
+
+// Per-launch times of the forward passes recorded since profiling was enabled, in launch order
+// (35 per forward: conv_in, then alternating companions and convolutions, conv_out, place).
+// Returns the number of launches written (<= cap); kind_out[i]: 0 tcgen05 conv (TMA-fed), 2 other.
+extern "C" int isg_unet_plan_profile_launches(isg_unet_plan *plan, double *ms_out, int *kind_out, int cap) {
+    if (!plan || !ms_out) return 0;
+    int n = 0;
+    for (size_t s = 0; s + 1 < plan->ev_used && n < cap; s += 2) {
+        if (plan->ev_kind[s / 2] == 1) continue;                  // the whole-forward scope
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, plan->ev[s], plan->ev[s + 1]) != cudaSuccess) break;
+        ms_out[n] = ms;
+        if (kind_out) kind_out[n] = plan->ev_kind[s / 2];
+        ++n;
+    }
+    return n;
 }
 
 extern "C" double isg_unet_plan_flops(const isg_unet_plan *plan) { return plan ? plan->flops : 0.0; }

@@ -52,6 +52,12 @@ namespace isg {
 struct ConvGeom {
     int N, D, H, W;              // batch (chunks) and spatial extents (in == out)
     int P, Ht, Wt;               // patch pitch, patch rows, valid outputs per row
+    int flat;                    // 1: band-flat tiling -- a tile is 128 CONSECUTIVE positions f = y*P + x' of a
+                                 // column band (P = Wt + 2 wide, all H rows), tile fb covers f in [128 fb, 128 fb + 128);
+                                 // the plane slot holds the Ht + 2 padded rows from y0 = 128 fb / P on, and every
+                                 // tap is still one constant row shift (dy*P + dx) of the A descriptor.  No rows are
+                                 // lost to patch-height quantisation: only the 2 halo columns per row and the last
+                                 // tile of a band are idle.  tiles_h = tiles per band = ceil(H*P / 128).
     int tiles_w, tiles_h;
     int T;                       // output planes (accumulators) per group
     int nsets;                   // 1: one accumulator set; 2: groups alternate between two sets, so the
@@ -203,7 +209,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         if ((g.debug & 2) && grp != (int)blockIdx.x) { mbar_arrive(&plane_full[pi]); continue; }
                         mbar_expect_tx(&plane_full[pi], (uint32_t)g.plane_rows * RB);
                         tma_load_5d(a_smem + (size_t)pi * g.plane_bytes, tm, &plane_full[pi], c,
-                                    wb * g.Wt - 1, hb * g.Ht - 1, d0 - 1 + pi, n);
+                                    wb * g.Wt - 1, (g.flat ? (hb * 128) / g.P : hb * g.Ht) - 1, d0 - 1 + pi, n);
                     }
                     ph ^= (1u << (tg + 2)) - 1u;
                 }
@@ -268,7 +274,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t cy = (uint32_t)g.P * U;
             const uint32_t plane_units = (uint32_t)g.plane_bytes >> 4;
             const uint32_t b_tap_units = (uint32_t)(g.cout * CBLK * 2) >> 4;
-            const uint32_t a_lo = d_lo | (smem_u32(a_smem) >> 4);
+            const uint32_t a_lo0 = d_lo | (smem_u32(a_smem) >> 4);
+            const int flat = g.flat, tiles_w = g.tiles_w, tiles_h = g.tiles_h, Pp = g.P;
             const uint32_t b_lo0 = d_lo | (smem_u32(b_smem) >> 4);
             const uint32_t b_stage_units = (uint32_t)g.b_stage_bytes >> 4;
             const uint32_t acc_cols = (uint32_t)g.acc_cols;
@@ -287,6 +294,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int tg = D - d0 < T ? D - d0 : T;
                 const int a0 = nsets == 2 ? (int)(gcount & 1u) * T : 0;   // accumulator set of this group
                 const uint32_t tmem_g = tmem_base + (uint32_t)a0 * acc_cols;
+                // band-flat tiling: the tile starts (128 fb) % P rows into the slot's first padded row
+                const uint32_t a_lo = a_lo0 + (flat ? (uint32_t)((((grp / tiles_w) % tiles_h) * 128) % Pp) * U : 0u);
                 if (b_resident) {
                     // ---- tile-major: all taps of a tile back to back (weights never move) ----
                     for (int kb = 0; kb < nkb; ++kb) {
@@ -393,7 +402,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int i = 0; i < 8; ++i) csum[i] = csq[i] = 0;
         int cur_n = -1;
         const int row = ew * 32 + lane;
-        const int hy = row / g.P, wx = row - hy * g.P;
+        int hy = row / g.P, wx = row - hy * g.P;
         auto flush = [&](int n) {
             if (n < 0) return;
 #pragma unroll
@@ -421,10 +430,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               flush(cur_n);
               cur_n = n;
           }
+          int h, w;
+          bool valid;
+          if (g.flat) {
+              const int f = hb * 128 + row;
+              h = f / g.P;
+              wx = f - h * g.P;
+              w = wb * g.Wt + wx;
+              valid = wx < g.Wt && h < g.H && w < g.W;
+          } else {
+              h = hb * g.Ht + hy;
+              w = wb * g.Wt + wx;
+              valid = hy < g.Ht && wx < g.Wt && h < g.H && w < g.W;
+          }
           for (int ti = 0; ti < tg; ++ti) {
             const int d = d0 + ti;
-            const int h = hb * g.Ht + hy, w = wb * g.Wt + wx;
-            const bool valid = hy < g.Ht && wx < g.Wt && h < g.H && w < g.W;
             const size_t vox = (((size_t)n * g.D + d) * g.H + h) * g.W + w;
             mbar_wait(&acc_full[a0 + ti], (acc_ph >> (a0 + ti)) & 1u);
             tc_fence_after();
