@@ -329,7 +329,25 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
                make_act_map(&t.tmA1, src1, 32, z.W, z.H, z.D, z.N, 32, ZR_P, ZR_HT) &&
                make_w_map_zring(&t.tmB, p->packed + p->L.w[i], cin);
     }
-    const int cblk = (c0 % 64 == 0 && (c1 % 64 == 0)) ? 64 : 32;
+    // Channel block of the K loop (= shared-memory row: 64 channels -> 128-byte swizzle, 32 -> 64-byte).
+    // Measured per layer on B200 (profiles/r02_notes.md): 32-channel blocks win for the plain layers
+    // with Cout <= 128 (half-size plane slots leave room for G = 3 / 9 taps per weight stage and for
+    // band-flat tiles: c2.conv1 1.15 -> 1.00 ms, c5_0.conv0 1.24 -> 1.11, c6_0.conv0 1.34 -> 1.21, c1.conv1
+    // 1.43 -> 1.31), 64-channel blocks for Cout = 256 (c3.conv1 1.06 vs 1.28 ms) and for the dx-fold layer
+    // (c7_0.conv0 1.31 vs 1.75 ms).  ISG_CONV_CBLK = "<layer index>:<32|64>,..." overrides (diagnosis).
+    int cblk = (c0 % 64 == 0 && (c1 % 64 == 0)) ? 64 : 32;
+    const bool fold_layer = cout_pad(i) <= 32 && p->W[l] >= 100;
+    if (cout_pad(i) <= 128 && !fold_layer) cblk = 32;
+    if (const char *ov = getenv("ISG_CONV_CBLK")) {
+        char key[16];
+        snprintf(key, sizeof key, ",%d:", i);
+        std::string lst = std::string(",") + ov + ",";
+        const size_t at = lst.find(key);
+        if (at != std::string::npos) {
+            const int v = atoi(lst.c_str() + at + strlen(key));
+            if (v == 32 || (v == 64 && c0 % 64 == 0 && c1 % 64 == 0)) cblk = v;
+        }
+    }
     t.cblk = cblk;
     ConvGeom &g = t.g;
     g.N = p->N; g.D = p->D[l]; g.H = p->H[l]; g.W = p->W[l];
