@@ -252,6 +252,15 @@ void isg_unet_plan_destroy(isg_unet_plan *plan);
 /* frame (Z,Y,X) float32 -> feats (5,Z,Y,X) float32: every voxel written by exactly
  * one chunk's cropped interior (predict.py:89-95). */
 int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream);
+/* The same with the input normalisation of segment_single_volume (vol /= max, segmentation.py:889)
+ * fused into the first kernel's loads: every voxel is divided by norm_max[0] (device float, e.g.
+ * minmax_out + 1 of isg_frame_minmax) -- bit-identical to isg_frame_divide_by_max + forward.
+ * `frame` may then be PINNED HOST memory mapped into the device address space (cudaHostAlloc /
+ * cudaHostRegister with unified addressing): the chunks are staged straight from the pinned
+ * volume, no H2D copy of the frame ("zero-copy").  Measured on B200 against the copy-engine path
+ * in profiles/r02_notes.md. */
+int isg_unet_forward_chunks_norm(isg_unet_plan *plan, const float *frame, const float *norm_max,
+                                 float *feats, void *stream);
 /* fp16 range guard.  Filters are divided by a per-output-channel power of two at pack time (the
  * train-mode BatchNorm that follows every convolution cancels it; BN_EPS is rescaled to match), so
  * the fp16 weights and pre-BatchNorm activations stay O(1) for any filter scale.  Should an
@@ -275,7 +284,7 @@ double isg_unet_plan_flops(const isg_unet_plan *plan);
  * object): enable, run forwards, synchronise the stream, read.
  * out[5] = {ms in tcgen05 convolutions, #tcgen05 launches, ms of whole forwards, #forwards,
  *           algorithmic FLOPs of the tcgen05 convolutions of ONE forward}. */
-int isg_unet_plan_profile(isg_unet_plan *plan, int enable);
+int isg_unet_plan_profile(isg_unet_plan *plan, int enable);   /* 0 off, 1 tcgen05 convs + whole forward, 2 every launch */
 int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out);
 /* per-launch times (ms) of the recorded forward passes in launch order, 35 launches per forward;
  * kind_out (nullable): 0 = TMA-fed tcgen05 convolution, 2 = any other kernel.  Returns the count. */

@@ -63,6 +63,7 @@ SIGNATURES = {
     'isg_unet_plan_overflowed': (_i32, [_vp]),
     'isg_unet_plan_clear_overflow': (_i32, [_vp, _vp]),
     'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),
+    'isg_unet_forward_chunks_norm': (_i32, [_vp, _vp, _vp, _vp, _vp]),
     'isg_unet_debug_activation': (_i32, [_vp, _vp, _c.c_char_p, _i32, _vp, _i64, _vp]),
     'isg_unet_plan_flops': (_c.c_double, [_vp]),
     'isg_unet_plan_profile': (_i32, [_vp, _i32]),

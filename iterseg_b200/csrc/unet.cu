@@ -230,9 +230,9 @@ static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
     const int N = p->N;
     auto vox = [&](int l) { return (size_t)N * p->D[l] * p->H[l] * p->W[l]; };
     static const int CH[5] = {32, 64, 128, 256, 256};
-    p->starts = cv.take<int>(N * 3);
-    p->crop_lo = cv.take<int>(N * 3);
-    p->crop_hi = cv.take<int>(N * 3);
+    p->starts = cv.take<int>(N * 9);                  // starts | crop_lo | crop_hi, one upload per forward
+    p->crop_lo = p->starts ? p->starts + 3 * N : nullptr;
+    p->crop_hi = p->starts ? p->starts + 6 * N : nullptr;
     for (int l = 0; l < 5; ++l) {
         p->raw[l] = cv.take<__half>(vox(l) * CH[l]);
         p->act[l] = cv.take<__half>(vox(l) * CH[l]);
@@ -496,7 +496,9 @@ struct ProfScope {
     cudaStream_t st;
     size_t slot;
     ProfScope(isg_unet_plan *plan, int kind, cudaStream_t s) : p(plan), st(s), slot((size_t)-1) {
-        if (!p->profiling) return;
+        // level 1: the TMA-fed tcgen05 convolutions and the whole forward (bench.py's live roofline);
+        // level 2: every launch (scripts/time_unet.py)
+        if (!p->profiling || (kind == 2 && p->profiling < 2)) return;
         if (p->ev_used + 2 > p->ev.size()) {
             cudaEvent_t a, b;
             cudaEventCreate(&a);
@@ -611,7 +613,8 @@ static inline dim3 egrid(size_t work, int N) {
 }
 
 // run the network up to and including conv `stop` (17 = everything incl. placement)
-static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop, cudaStream_t st) {
+static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop, cudaStream_t st,
+                   const float *norm_max = nullptr) {
     const int N = p->N;
     auto run_tc = [&](int i) {
         ProfScope ps(p, 0, st);
@@ -628,9 +631,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
         const size_t nb = sizeof(int) * 3 * (size_t)N;
         static const bool once = getenv("ISG_TABLES_ONCE") != nullptr;      // diagnosis only (unsafe with shared workspaces)
         if (!(once && p->tabs_dirty == 0)) {
-        ISG_CUDA(cudaMemcpyAsync(p->starts, p->tabs_host, nb, cudaMemcpyHostToDevice, st));
-        ISG_CUDA(cudaMemcpyAsync(p->crop_lo, p->tabs_host + 3 * N, nb, cudaMemcpyHostToDevice, st));
-        ISG_CUDA(cudaMemcpyAsync(p->crop_hi, p->tabs_host + 6 * N, nb, cudaMemcpyHostToDevice, st));
+        ISG_CUDA(cudaMemcpyAsync(p->starts, p->tabs_host, 3 * nb, cudaMemcpyHostToDevice, st));
         ISG_CUDA(cudaEventRecord(p->tabs_ev, st));
         p->tabs_ev_pending = 1;
         p->tabs_dirty = 0;
@@ -647,7 +648,7 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
     {
         ProfScope ps(p, 2, st);
         ThinArgs a{};
-        a.src = frame; a.starts = p->starts; a.Y = p->Y; a.X = p->X;
+        a.src = frame; a.norm_max = norm_max; a.starts = p->starts; a.Y = p->Y; a.X = p->X;
         a.wgt = reinterpret_cast<const float *>(pk + L.w[0]);
         a.out = p->raw[0]; a.stats = p->stats[0];
         a.N = N; a.D = p->D[0]; a.H = p->H[0]; a.W = p->W[0];
@@ -974,7 +975,7 @@ extern "C" int isg_unet_plan_set_chunks(isg_unet_plan *plan, const int32_t *star
 
 extern "C" int isg_unet_plan_profile(isg_unet_plan *plan, int enable) {
     ISG_REQUIRE(plan, ISG_ERR_ARG, "isg_unet_plan_profile: null plan");
-    plan->profiling = enable ? 1 : 0;
+    plan->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     plan->ev_used = 0;
     return ISG_OK;
 }
@@ -1022,6 +1023,14 @@ extern "C" int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, 
                 "isg_unet_forward_chunks: an earlier forward pass of this plan overflowed the fp16 range of the "
                 "pre-BatchNorm activations (its feature volume is invalid); isg_unet_plan_clear_overflow re-arms");
     return forward(plan, frame, feats, 17, (cudaStream_t)stream);
+}
+
+extern "C" int isg_unet_forward_chunks_norm(isg_unet_plan *plan, const float *frame, const float *norm_max,
+                                            float *feats, void *stream) {
+    ISG_REQUIRE(plan && frame && feats && norm_max, ISG_ERR_ARG, "isg_unet_forward_chunks_norm: null pointer");
+    ISG_REQUIRE(!isg_unet_plan_overflowed(plan), ISG_ERR_OVERFLOW,
+                "isg_unet_forward_chunks_norm: an earlier forward pass of this plan overflowed the fp16 range");
+    return forward(plan, frame, feats, 17, (cudaStream_t)stream, norm_max);
 }
 
 extern "C" int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame, const char *name,

@@ -37,7 +37,11 @@ __host__ __device__ constexpr size_t thin_smem_bytes() {
 }
 
 struct ThinArgs {
-    const float *src;                     // frame (Z,Y,X) fp32
+    const float *src;                     // frame (Z,Y,X) fp32 (device memory, or pinned host memory mapped
+                                          // into the device address space: "zero-copy" staging)
+    const float *norm_max;                // nullable: every input voxel is divided by norm_max[0] on its way in
+                                          // (vol /= max, segmentation.py:889; IEEE division, bit-identical to
+                                          // isg_frame_divide_by_max followed by a plain load)
     const int *starts;                    // [N][3] chunk origins
     int Y, X;
     const float *wgt;                     // [27][32] fp32
@@ -126,6 +130,7 @@ conv_in_tc_kernel(const ThinArgs a) {
         int n, d, h0, w0;
         decode(u, n, d, h0, w0);
         const int z0 = __ldg(a.starts + n * 3 + 0), y0 = __ldg(a.starts + n * 3 + 1), x0 = __ldg(a.starts + n * 3 + 2);
+        const float dmax = a.norm_max ? __ldg(a.norm_max) : 1.0f;
         float v[HSLOTS];
 #pragma unroll
         for (int j = 0; j < HSLOTS; ++j) {
@@ -133,6 +138,10 @@ conv_in_tc_kernel(const ThinArgs a) {
             v[j] = 0.0f;
             if (h_off[j] >= 0 && dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
                 v[j] = __ldg(a.src + ((size_t)(z0 + dd) * a.Y + (y0 + hh)) * a.X + (x0 + ww));
+        }
+        if (a.norm_max) {
+#pragma unroll
+            for (int j = 0; j < HSLOTS; ++j) v[j] = __fdiv_rn(v[j], dmax);
         }
 #pragma unroll
         for (int j = 0; j < HSLOTS; ++j)

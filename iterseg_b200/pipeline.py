@@ -36,8 +36,10 @@ class FramePipeline:
         # kernels leave `post_sms` SMs to the flood while both are in flight
         _lib.check(_lib.load().isg_set_post_sm_reservation(self.post_sms if on else 0), 'isg_set_post_sm_reservation')
 
-    def submit(self, frame):
-        """Enqueue the U-Net of one (Z,Y,X) float32 device frame; returns its slot index."""
+    def submit(self, frame, norm_max=None):
+        """Enqueue the U-Net of one (Z,Y,X) float32 device frame; returns its slot index.
+        norm_max: 1-element float32 device tensor -> the frame is divided by it inside the first
+        kernel (and may then be a pinned HOST tensor, read in place)."""
         k = self.n_in % len(self.slots)
         slot = self.slots[k]
         assert not slot['busy'], 'pipeline full: collect() a frame first'
@@ -46,9 +48,11 @@ class FramePipeline:
         self._reserve(self.n_in > self.n_out)          # a post stage will run beside this U-Net
         with torch.cuda.stream(self.s_unet):
             self.s_unet.wait_event(slot['ev_post'])     # the slot's previous post stage has read feats
-            predict.predict_frame_device(self.net, frame, self.chunk_size, self.margin, out=slot['feats'])
+            predict.predict_frame_device(self.net, frame, self.chunk_size, self.margin, out=slot['feats'],
+                                         norm_max=norm_max)
             slot['ev_unet'].record(self.s_unet)
-        frame.record_stream(self.s_unet)
+        if frame.is_cuda:
+            frame.record_stream(self.s_unet)
         slot['busy'] = True
         self.n_in += 1
         return k
@@ -143,10 +147,20 @@ class SeriesPipeline:
     N_IN = 4        # pinned input buffers / device frame buffers
     N_OUT = 4       # device crop buffers / pinned output buffers (= frames the writer threads may hold)
 
-    def __init__(self, core, normalise=True):
+    def __init__(self, core, normalise=True, staging=None):
+        import os
         import queue
         self.core, self.dev, self.shape = core, core.dev, core.shape
         self.normalise = normalise
+        # input staging of the affinity path (BASELINE.json north_star (1)):
+        #   'copy'     one H2D copy per frame on the copy engine, min/max, divide kernel, U-Net
+        #   'fused'    the same copy, the division fused into the first U-Net kernel's loads   (default)
+        #   'zerocopy' no copy: min/max and the first U-Net kernel read the pinned frame in place
+        # measured on B200 in profiles/r02_notes.md; the copy engine wins (it runs beside the previous
+        # frame's kernels, while zero-copy reads put PCIe latency inside the first kernel)
+        self.staging = staging or os.environ.get('ISG_INPUT_STAGING', 'fused')
+        if not isinstance(core, FramePipeline) or not normalise:
+            self.staging = 'copy'
         self.lib = _lib.load()
         n = 1
         for s in self.shape:
@@ -172,6 +186,8 @@ class SeriesPipeline:
         for o in range(self.N_OUT):
             self.free_out.put(o)
         self.n_staged = 0
+        self.closed = False
+        self.held = __import__('collections').deque()      # zero-copy: pinned buffers of the frames in flight
         torch.cuda.synchronize(self.dev)
 
     # ---- host side of the input (loader threads) -------------------------------------------
@@ -188,10 +204,19 @@ class SeriesPipeline:
             if self.free_in.empty() and self._n_in_alloc < self.N_IN:
                 self._n_in_alloc += 1
                 buf = torch.empty(self.shape, dtype=torch.float32).pin_memory()
-        if buf is None:
-            buf = self.free_in.get()
+        import queue
+        while buf is None:                                       # never block for ever: close() wakes us up
+            if self.closed:
+                raise RuntimeError('series pipeline closed')
+            try:
+                buf = self.free_in.get(timeout=0.2)
+            except queue.Empty:
+                pass
         np.copyto(buf.numpy(), np.asarray(src), casting='unsafe')
         return 'buf', buf
+
+    def close(self):
+        self.closed = True
 
     # ---- main thread ---------------------------------------------------------------------------
     def h2d(self, loaded):
@@ -201,8 +226,12 @@ class SeriesPipeline:
         st = self.stage[j]
         with torch.cuda.device(self.dev), torch.cuda.stream(self.s_copy):
             self.s_copy.wait_event(st['ev_consumed'])           # the U-Net that read this buffer last
-            st['frame'].copy_(host, non_blocking=True)
-            _lib.check(self.lib.isg_frame_minmax(st['frame'].data_ptr(), self.nvox, st['mm'].data_ptr(),
+            if self.staging == 'zerocopy':
+                st['src'] = host
+            else:
+                st['frame'].copy_(host, non_blocking=True)
+                st['src'] = st['frame']
+            _lib.check(self.lib.isg_frame_minmax(st['src'].data_ptr(), self.nvox, st['mm'].data_ptr(),
                                                  st['scratch'].data_ptr(), st['scratch'].numel(),
                                                  _lib.stream_ptr()), 'isg_frame_minmax')
             st['mm_host'].copy_(st['mm'], non_blocking=True)
@@ -217,13 +246,20 @@ class SeriesPipeline:
         st = self.stage[j]
         st['ev_stage'].synchronize()                            # copy stream only
         kind, host = st.pop('host')
-        if kind == 'buf':
+        zero = self.normalise and float(st['mm_host'][0]) == 0.0
+        if self.staging == 'zerocopy' and not zero:
+            self.held.append((kind, host, st['ev_consumed']))   # read in place by the U-Net: released in collect()
+        elif kind == 'buf':
             self.free_in.put(host)
-        if self.normalise and float(st['mm_host'][0]) == 0.0:
+        if zero:
             return False
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.device(self.dev):
-            if self.normalise:
+            if self.staging in ('fused', 'zerocopy'):
+                with torch.cuda.stream(self.core.s_unet):
+                    self.core.s_unet.wait_stream(cur)
+                    self.core.submit(st['src'], norm_max=st['mm'][1:2])
+            elif self.normalise:
                 with torch.cuda.stream(self.core.s_unet):
                     self.core.s_unet.wait_stream(cur)
                     _lib.check(self.lib.isg_frame_divide_by_max(st['frame'].data_ptr(), self.nvox,
@@ -244,6 +280,11 @@ class SeriesPipeline:
         o = self.free_out.get()                                  # back-pressure from the writers
         out = self.outs[o]
         lab, counts = self.core.collect()
+        if self.held:                                            # zero-copy: this frame's U-Net has read its input
+            kind, host, ev = self.held.popleft()
+            ev.synchronize()
+            if kind == 'buf':
+                self.free_in.put(host)
         Z, Y, X = self.shape
         with torch.cuda.device(self.dev):
             with torch.cuda.stream(self.core.s_post):

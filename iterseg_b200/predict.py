@@ -104,17 +104,17 @@ def _chunk_tables(shape, chunk_size, margin):
     return st, np.ascontiguousarray(cr[:, :, 0]), np.ascontiguousarray(cr[:, :, 1])
 
 
-def predict_frame_device(unet, frame, chunk_size, margin, out=None, tables=None):
+def predict_frame_device(unet, frame, chunk_size, margin, out=None, tables=None, norm_max=None):
     """All chunks of one frame on the device: frame (Z,Y,X) float32 CUDA tensor ->
     (5,Z,Y,X) float32 CUDA tensor.  `tables` = (starts, crop_lo, crop_hi) restricts the
     work to a subset of the global chunk list (spatial sharding)."""
     st, lo, hi = tables if tables is not None else _chunk_tables(frame.shape, chunk_size, margin)
     if out is None:
-        out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=frame.device)
+        out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=unet.device)
     per = chunks_per_batch(unet, chunk_size, len(st))
     for b in range(0, len(st), per):
         sl = slice(b, b + per)
-        unet.forward_chunks(frame, chunk_size, st[sl], lo[sl], hi[sl], out=out)
+        unet.forward_chunks(frame, chunk_size, st[sl], lo[sl], hi[sl], out=out, norm_max=norm_max)
     return out
 
 

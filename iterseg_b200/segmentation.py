@@ -288,9 +288,11 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
     n_steps = (int(data.shape[0]) + world - 1) // world        # lock-step count when offsets are global
     offsets = idist.LabelOffsets(rank, world, dev, config.get('process_group')) if want_offsets else None
 
+    depth = int(os.environ.get('ISG_PIPE_DEPTH', '2')) if kind == 'affinity' else 2   # U-Nets submitted ahead of the post stage
+
     def make_pipe():
         if kind == 'affinity':
-            core = FramePipeline(config['unet'], shape, chunk, margin)
+            core = FramePipeline(config['unet'], shape, chunk, margin, depth=depth)
         else:
             core = DogCore(shape, dev, min_sigma=config['min_sigma'], max_sigma=config['max_sigma'],
                            threshold=config['threshold'])
@@ -383,7 +385,7 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
                         raise NotImplementedError('a warm restart of a globally numbered series is not supported')
                     continue
                 staged.append((t, pipe.h2d(res)))
-            if staged and len(running) < 2:                      # a U-Net slot is free
+            if staged and len(running) < depth:                  # a U-Net slot is free
                 t, j = staged.popleft()
                 if pipe.submit(j):
                     running.append(t)
@@ -406,6 +408,7 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
         if offsets is not None:
             LAST_COUNTS['global_total'] = offsets.total
     finally:
+        pipe.close()                                             # wakes loader threads waiting for a buffer
         loaders.shutdown(wait=False, cancel_futures=True)
         writers.shutdown(wait=True)
         torch.cuda.synchronize(dev)

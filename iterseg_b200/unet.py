@@ -193,23 +193,31 @@ class UNet(nn.Module):
         self._plans[key] = p                                       # most recently used last
         return p
 
-    def forward_chunks(self, frame, chunk_shape, starts, crop_lo, crop_hi, out=None):
+    def forward_chunks(self, frame, chunk_shape, starts, crop_lo, crop_hi, out=None, norm_max=None):
         """frame (Z,Y,X) float32 CUDA tensor -> (5,Z,Y,X) float32: the cropped interior of
-        every chunk's prediction is placed into `out` (process_chunks, predict.py:64-96)."""
-        assert frame.is_cuda and frame.dtype == torch.float32 and frame.is_contiguous()
+        every chunk's prediction is placed into `out` (process_chunks, predict.py:64-96).
+        norm_max: optional 1-element float32 CUDA tensor; the frame is divided by it inside the first
+        kernel (vol /= max, segmentation.py:889) and may then be a PINNED HOST tensor read in place
+        ("zero-copy" staging; `out` must be given)."""
+        assert frame.dtype == torch.float32 and frame.is_contiguous()
+        assert frame.is_cuda or (norm_max is not None and frame.is_pinned() and out is not None)
         p = self.plan(frame.shape, chunk_shape, len(starts))
         p.set_chunks(starts, crop_lo, crop_hi)
         if out is None:
             out = torch.zeros((5,) + tuple(frame.shape), dtype=torch.float32, device=frame.device)
-        with torch.cuda.device(frame.device):
+        with torch.cuda.device(out.device):
             cur = torch.cuda.current_stream()
             # forward passes share the workspace: whatever stream this one is enqueued on, it starts
             # after the previous one has finished (a device-side wait, nothing blocks on the host)
             if self._ws_event is not None:
                 cur.wait_event(self._ws_event)
             p.workspace.record_stream(cur)
-            rc = _lib.load().isg_unet_forward_chunks(p.ptr, frame.data_ptr(), out.data_ptr(),
-                                                     _lib.stream_ptr())
+            if norm_max is None:
+                rc = _lib.load().isg_unet_forward_chunks(p.ptr, frame.data_ptr(), out.data_ptr(),
+                                                         _lib.stream_ptr())
+            else:
+                rc = _lib.load().isg_unet_forward_chunks_norm(p.ptr, frame.data_ptr(), norm_max.data_ptr(),
+                                                              out.data_ptr(), _lib.stream_ptr())
             _lib.check(rc, 'isg_unet_forward_chunks')
             if self._ws_event is None:
                 self._ws_event = torch.cuda.Event()

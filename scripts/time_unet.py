@@ -32,7 +32,7 @@ plan = list(net._plans.values())[0]
 import ctypes
 from iterseg_b200 import _lib
 lib = _lib.load()
-lib.isg_unet_plan_profile(plan.ptr, 1)
+lib.isg_unet_plan_profile(plan.ptr, 2)
 for _ in range(reps):
     predict.predict_frame_device(net, vol, (10, 256, 256), (1, 64, 64), out=out)
 torch.cuda.synchronize()

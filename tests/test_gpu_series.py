@@ -162,3 +162,20 @@ def test_capped_flood_workspace_fails_loudly_then_succeeds():
     want = np.zeros((10, 98, 98), np.uint32)
     opost.segment_output_image(feats_h, out=want.ravel())
     assert np.array_equal(labels.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize('staging', ['fused', 'zerocopy'])
+def test_input_staging_modes_are_bit_identical(net, data, monkeypatch, staging):
+    """north_star (1): the chunks staged straight from the pinned volume (`zerocopy`: no H2D copy, the
+    first U-Net kernel and the min/max kernel read the pinned frame in place, `vol /= max` fused into
+    the loads) and the copy-engine path with the fused division give the labels of the default path."""
+    from iterseg_b200 import segmentation
+    _, want = _plain(net, data, monkeypatch)
+    monkeypatch.setenv('ISG_INPUT_STAGING', staging)
+    cfg = {'unet': net, 'output_volume': np.zeros(1)}
+    for src in (torch.from_numpy(data.copy()).pin_memory().numpy(), data.astype(np.float64)):
+        out = np.zeros(data.shape, np.int32)
+        order = list(segmentation.segmentation_loop(None, src, CHUNK, MARGIN, out,
+                                                    segmentation.affinity_watershed_for_chunks, cfg))
+        assert order == list(range(len(data)))
+        assert np.array_equal(out, want)
