@@ -188,6 +188,8 @@ int isg_relabel_by_keys(uint32_t *labels, int64_t n, const unsigned long long *l
  *   distance_out optional (Z+2,Y+2,X+2) float64: ndi.distance_transform_edt(padded volume)
  *   counts_out   device int64[4]: {peak candidates, blobs after pruning, marker voxels, 0}
  */
+#define ISG_DOG_MAX_SIGMAS 9     /* sigma_list of blob_dog: up to 8 DoG layers */
+#define ISG_GAUSS_MAX_RADIUS 27  /* sigma <= 6.8 at truncate = 4 */
 typedef struct {
     double weights[4][12];
     int radius[4];
@@ -195,8 +197,24 @@ typedef struct {
     float scale_factor;
     int prune_d2;
     int prune_radius;
+    /* multi-layer blob_dog (max_sigma / min_sigma >= sigma_ratio): n_layers = k >= 2 DoG layers from the
+     * k + 1 'reflect' Gaussians of sigma_list[i] = min_sigma * sigma_ratio^i; 3^4 maxima over (z,y,x,layer);
+     * _prune_blobs with per-blob sigma: pairs (i < j, peak order) closer than 2 * max(sigma) * sqrt(3), walked
+     * in lexicographic order, the blob that is not larger dies when the spheres overlap by more than
+     * `overlap`.  n_layers <= 1 selects the single-layer fields above (the default configuration). */
+    int n_layers;
+    double overlap;
+    double layer_sigma[ISG_DOG_MAX_SIGMAS];
+    int layer_radius[ISG_DOG_MAX_SIGMAS];
+    double layer_weights[ISG_DOG_MAX_SIGMAS][ISG_GAUSS_MAX_RADIUS + 1];
+    /* the two 'nearest' Gaussians of the mask (min_sigma, max_sigma) when n_layers > 1: max_sigma may
+     * need a radius beyond the 11 of weights[0..1] */
+    int mask_radius[2];
+    double mask_weights[2][ISG_GAUSS_MAX_RADIUS + 1];
 } isg_dog_params;
 size_t isg_dog_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds);
+/* workspace for n_layers DoG layers (n_layers <= 1: the same as isg_dog_workspace_bytes) */
+size_t isg_dog_workspace_bytes_layers(int64_t z, int64_t y, int64_t x, int64_t max_seeds, int n_layers);
 int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int64_t x, const isg_dog_params *params,
                          uint32_t *labels, uint8_t *mask_out, double *distance_out, int64_t max_seeds,
                          int64_t *counts_out, void *workspace, size_t workspace_bytes, void *stream);

@@ -21,9 +21,16 @@ class PostParams(_c.Structure):
                 ('own_z1', _i32), ('open_faces', _i32), ('seed_keys_out', _vp)]
 
 
+DOG_MAX_SIGMAS, GAUSS_MAX_RADIUS = 9, 27
+
+
 class DogParams(_c.Structure):
     _fields_ = [('weights', (_c.c_double * 12) * 4), ('radius', _i32 * 4), ('threshold', _f32),
-                ('scale_factor', _f32), ('prune_d2', _i32), ('prune_radius', _i32)]
+                ('scale_factor', _f32), ('prune_d2', _i32), ('prune_radius', _i32),
+                ('n_layers', _i32), ('overlap', _c.c_double), ('layer_sigma', _c.c_double * DOG_MAX_SIGMAS),
+                ('layer_radius', _i32 * DOG_MAX_SIGMAS),
+                ('layer_weights', (_c.c_double * (GAUSS_MAX_RADIUS + 1)) * DOG_MAX_SIGMAS),
+                ('mask_radius', _i32 * 2), ('mask_weights', (_c.c_double * (GAUSS_MAX_RADIUS + 1)) * 2)]
 
 
 # name -> (restype, argtypes); this table is also what the symbol-export test checks
@@ -49,6 +56,7 @@ SIGNATURES = {
     'isg_sort_keys_u64': (_i32, [_vp, _i64, _vp, _sz, _vp]),
     'isg_relabel_by_keys': (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     'isg_dog_workspace_bytes': (_sz, [_i64, _i64, _i64, _i64]),
+    'isg_dog_workspace_bytes_layers': (_sz, [_i64, _i64, _i64, _i64, _i32]),
     'isg_dog_blob_segment': (_i32, [_vp, _i64, _i64, _i64, _c.POINTER(DogParams), _vp, _vp, _vp, _i64, _vp,
                                     _vp, _sz, _vp]),
     'isg_metrics_workspace_bytes': (_sz, [_i64, _i64]),

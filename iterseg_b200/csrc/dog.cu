@@ -94,6 +94,138 @@ dog_peak_kernel(const float *__restrict__ cs, uint32_t Z, uint32_t Y, uint32_t X
     if (__any_sync(0xFFFFFFFFu, saw_nonmax) && (threadIdx.x & 31) == 0) atomicOr(nontrivial, 1u);
 }
 
+// multi-layer: 3^4 maxima over (z, y, x, layer) of the cube [layer][z][y][x] ('nearest' = clamped window
+// on all four axes), value > thr; candidate key = (~ord(value) << 32) | (voxel * K + layer), i.e. ties in
+// argwhere order of the (z, y, x, layer) array; max_layer = the largest layer index that holds a peak
+__global__ void __launch_bounds__(256)
+dog_peak4_kernel(const float *__restrict__ cube, int K, uint32_t Z, uint32_t Y, uint32_t X, float thr,
+                 uint64_t *__restrict__ cand, uint32_t cap, uint32_t *__restrict__ n_cand,
+                 uint32_t *__restrict__ nontrivial, uint32_t *__restrict__ max_layer) {
+    const uint64_t n = (uint64_t)Z * Y * X;
+    const uint64_t total = n * (uint64_t)K;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool saw_nonmax = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = (int)(i / n);
+        const uint64_t v = i - (uint64_t)k * n;
+        const uint32_t x = (uint32_t)(v % X);
+        const uint64_t t = v / X;
+        const uint32_t y = (uint32_t)(t % Y), z = (uint32_t)(t / Y);
+        const float c = cube[i];
+        bool is_max = true;
+        const int k0 = k ? k - 1 : 0, k1 = k + 1 < K ? k + 1 : K - 1;
+        const uint32_t z0 = z ? z - 1 : 0, z1 = z + 1 < Z ? z + 1 : Z - 1;
+        const uint32_t y0 = y ? y - 1 : 0, y1 = y + 1 < Y ? y + 1 : Y - 1;
+        const uint32_t x0 = x ? x - 1 : 0, x1 = x + 1 < X ? x + 1 : X - 1;
+        if (c > thr || !saw_nonmax) {                       // below the threshold only the "constant cube" test needs it
+            for (int kk = k0; kk <= k1; ++kk)
+                for (uint32_t zz = z0; zz <= z1; ++zz)
+                    for (uint32_t yy = y0; yy <= y1; ++yy) {
+                        const float *row = cube + (uint64_t)kk * n + ((uint64_t)zz * Y + yy) * X;
+                        for (uint32_t xx = x0; xx <= x1; ++xx) is_max &= !(__ldg(row + xx) > c);
+                    }
+            if (!is_max) saw_nonmax = true;
+            if (is_max && c > thr) {
+                const uint32_t slot = atomicAdd(n_cand, 1u);
+                if (slot < cap) cand[slot] = ((uint64_t)(~f32_ord(c)) << 32) | (v * (uint64_t)K + (uint64_t)k);
+                atomicMax(max_layer, (uint32_t)k);
+            }
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, saw_nonmax) && (threadIdx.x & 31) == 0) atomicOr(nontrivial, 1u);
+}
+
+// _prune_blobs with per-blob sigma, one CTA.  Blobs in peak order; a pair (i, j), i < j, is "close" when
+// sqrt(d2) <= dist; pairs are walked in lexicographic order and use the CURRENT sigmas (a dead blob has
+// sigma 0, overlaps nothing it could kill and is skipped).  For a live blob i all its pairs are
+// evaluated in parallel: j* = the first close live j that kills i (overlap > thr and sigma_i <= sigma_j);
+// every close live j < j* (all of them when there is no j*) with overlap > thr and sigma_i > sigma_j dies.
+// O(N^2 / 1024) distance tests: milliseconds for the thousands of blobs of a frame.
+__device__ __forceinline__ double blob_overlap_frac(double s1, double s2, double d2) {
+    const double root3 = sqrt(3.0);
+    double r1 = __dmul_rn(s1, root3), r2 = __dmul_rn(s2, root3);
+    if (r2 > r1) { const double t = r1; r1 = r2; r2 = t; }
+    const double d = sqrt(d2);
+    if (d > __dadd_rn(r1, r2)) return 0.0;
+    if (d <= fabs(__dsub_rn(r1, r2))) return 1.0;
+    const double pi = 3.141592653589793;
+    const double a = __dsub_rn(__dadd_rn(r1, r2), d);
+    const double rm = __dsub_rn(r1, r2);
+    double poly = __dadd_rn(__dmul_rn(d, d), __dmul_rn(__dmul_rn(2.0, d), __dadd_rn(r1, r2)));
+    poly = __dsub_rn(poly, __dmul_rn(3.0, __dmul_rn(rm, rm)));
+    const double vol = __dmul_rn(__dmul_rn(__ddiv_rn(pi, __dmul_rn(12.0, d)), __dmul_rn(a, a)), poly);
+    const double mn = r1 < r2 ? r1 : r2;
+    const double full = __dmul_rn(__dmul_rn(__ddiv_rn(4.0, 3.0), pi), pow(mn, 3.0));
+    return __ddiv_rn(vol, full);
+}
+__global__ void __launch_bounds__(1024)
+blob_prune_multi_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n, int K,
+                        const uint32_t *__restrict__ nontrivial, uint32_t Y, uint32_t X,
+                        const double *__restrict__ sigmas, double dist, double thr,
+                        float *__restrict__ sig /* [n] scratch */, uint8_t *__restrict__ centroids,
+                        uint32_t *__restrict__ n_blobs) {
+    if (*nontrivial == 0) return;
+    __shared__ uint32_t jstar;
+    const uint64_t plane = (uint64_t)Y * X;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t id = cand_sorted[i] & 0xFFFFFFFFull;
+        sig[i] = (float)(int)(id % (uint64_t)K + 1);          // layer + 1 while alive, 0 when dead
+    }
+    __syncthreads();
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        if (sig[i] == 0.0f) continue;                          // uniform: written before the last barrier
+        if (threadIdx.x == 0) jstar = 0xFFFFFFFFu;
+        __syncthreads();
+        const uint64_t idi = cand_sorted[i] & 0xFFFFFFFFull;
+        const uint64_t vi = idi / (uint64_t)K;
+        const int zi = (int)(vi / plane), yi = (int)((vi % plane) / X), xi = (int)(vi % X);
+        const double si = sigmas[(int)sig[i] - 1];
+        uint32_t mine[4];                                      // this thread's close live js that i may kill
+        int n_mine = 0;
+        bool overflow = false;
+        for (uint32_t j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            const float sj_f = sig[j];
+            if (sj_f == 0.0f) continue;
+            const uint64_t vj = (cand_sorted[j] & 0xFFFFFFFFull) / (uint64_t)K;
+            const int dz = (int)(vj / plane) - zi, dy = (int)((vj % plane) / X) - yi, dx = (int)(vj % X) - xi;
+            const double d2 = (double)(dz * dz + dy * dy + dx * dx);
+            if (sqrt(d2) > dist) continue;
+            const double sj = sigmas[(int)sj_f - 1];
+            if (!(blob_overlap_frac(si, sj, d2) > thr)) continue;
+            if (si > sj) {
+                if (n_mine < 4) mine[n_mine++] = j; else overflow = true;
+            } else {
+                atomicMin(&jstar, j);
+            }
+        }
+        __syncthreads();
+        const uint32_t js = jstar;
+        for (int q = 0; q < n_mine; ++q)
+            if (mine[q] < js) sig[mine[q]] = 0.0f;
+        if (overflow) {                                        // more than 4 victims in one thread's stride: redo them
+            for (uint32_t j = i + 1 + threadIdx.x; j < n && j < js; j += blockDim.x) {
+                const float sj_f = sig[j];
+                if (sj_f == 0.0f) continue;
+                const uint64_t vj = (cand_sorted[j] & 0xFFFFFFFFull) / (uint64_t)K;
+                const int dz = (int)(vj / plane) - zi, dy = (int)((vj % plane) / X) - yi, dx = (int)(vj % X) - xi;
+                const double d2 = (double)(dz * dz + dy * dy + dx * dx);
+                if (sqrt(d2) > dist) continue;
+                const double sj = sigmas[(int)sj_f - 1];
+                if (blob_overlap_frac(si, sj, d2) > thr && si > sj) sig[j] = 0.0f;
+            }
+        }
+        if (threadIdx.x == 0 && js != 0xFFFFFFFFu) sig[i] = 0.0f;
+        __syncthreads();
+    }
+    uint32_t alive = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (sig[i] != 0.0f) {
+            centroids[(cand_sorted[i] & 0xFFFFFFFFull) / (uint64_t)K] = 1;
+            ++alive;
+        }
+    if (alive) atomicAdd(n_blobs, alive);
+}
+
 // blob index grid (rank + 1 in peak order) and the prune rule
 __global__ void blob_grid_kernel(const uint64_t *__restrict__ cand_sorted, uint32_t n,
                                  const uint32_t *__restrict__ nontrivial, uint32_t *__restrict__ grid) {
@@ -226,6 +358,9 @@ __global__ void dog_counts_kernel(const uint32_t *n_cand, const uint32_t *n_blob
 }
 
 struct DogBuffers {
+    float *cube;                   // multi-layer: [K][np] DoG layers
+    float *sig;                    // multi-layer: per-candidate state of the prune sweep
+    double *sigmas;                // multi-layer: sigma_list on the device
     float *vp, *ga, *gb, *gc;
     uint32_t *d2a, *d2b, *key, *grid, *flag, *rank;
     uint64_t *cand_a, *cand_b;
@@ -237,7 +372,10 @@ struct DogBuffers {
     FloodStageBuffers flood;
 };
 
-static void dog_carve(DogBuffers *b, Carver &cv, uint64_t np, int64_t max_seeds) {
+static void dog_carve(DogBuffers *b, Carver &cv, uint64_t np, int64_t max_seeds, int n_layers) {
+    b->cube = n_layers > 1 ? cv.take<float>(np * (uint64_t)n_layers) : nullptr;
+    b->sig = n_layers > 1 ? cv.take<float>(max_seeds) : nullptr;
+    b->sigmas = n_layers > 1 ? cv.take<double>(ISG_DOG_MAX_SIGMAS) : nullptr;
     b->vp = cv.take<float>(np);
     b->ga = cv.take<float>(np);
     b->gb = cv.take<float>(np);
@@ -282,9 +420,14 @@ using namespace isg;
 
 extern "C" size_t isg_dog_workspace_bytes(int64_t z, int64_t y, int64_t x, int64_t max_seeds) {
     if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0) return 0;
+    return isg_dog_workspace_bytes_layers(z, y, x, max_seeds, 1);
+}
+
+extern "C" size_t isg_dog_workspace_bytes_layers(int64_t z, int64_t y, int64_t x, int64_t max_seeds, int n_layers) {
+    if (z <= 0 || y <= 0 || x <= 0 || max_seeds <= 0 || n_layers >= ISG_DOG_MAX_SIGMAS) return 0;
     Carver cv(nullptr, 0);
     DogBuffers b;
-    dog_carve(&b, cv, (uint64_t)(z + 2) * (y + 2) * (x + 2), max_seeds);
+    dog_carve(&b, cv, (uint64_t)(z + 2) * (y + 2) * (x + 2), max_seeds, n_layers);
     return cv.off + 512;
 }
 
@@ -294,22 +437,36 @@ extern "C" int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int6
                                     void *workspace, size_t workspace_bytes, void *stream) {
     ISG_REQUIRE(vol && prm && labels && mask_out && counts_out, ISG_ERR_ARG, "isg_dog_blob_segment: null pointer");
     ISG_REQUIRE(z >= 1 && y >= 1 && x >= 1 && max_seeds >= 1, ISG_ERR_ARG, "bad extents");
-    for (int i = 0; i < 4; ++i)
+    const int K = prm->n_layers > 1 ? prm->n_layers : 1;
+    for (int i = 0; i < 4 && K == 1; ++i)
         ISG_REQUIRE(prm->radius[i] >= 0 && prm->radius[i] <= 11, ISG_ERR_ARG, "gaussian radius must be <= 11");
+    for (int i = 0; i < 2 && K > 1; ++i)
+        ISG_REQUIRE(prm->mask_radius[i] >= 0 && prm->mask_radius[i] <= ISG_GAUSS_MAX_RADIUS, ISG_ERR_ARG,
+                    "gaussian radius must be <= %d", ISG_GAUSS_MAX_RADIUS);
+    ISG_REQUIRE(K < ISG_DOG_MAX_SIGMAS, ISG_ERR_ARG, "isg_dog_blob_segment: at most %d DoG layers", ISG_DOG_MAX_SIGMAS - 1);
+    if (K > 1)
+        for (int i = 0; i <= K; ++i)
+            ISG_REQUIRE(prm->layer_radius[i] >= 0 && prm->layer_radius[i] <= ISG_GAUSS_MAX_RADIUS && prm->layer_sigma[i] > 0,
+                        ISG_ERR_ARG, "isg_dog_blob_segment: layer %d: gaussian radius must be <= %d", i, ISG_GAUSS_MAX_RADIUS);
     const uint32_t Z = (uint32_t)z + 2, Y = (uint32_t)y + 2, X = (uint32_t)x + 2;      // padded extents
     const uint64_t np = (uint64_t)Z * Y * X;
-    ISG_REQUIRE(np < 0xFFFFFFF0ull, ISG_ERR_OVERFLOW, "volume too large for 32-bit voxel ids");
+    ISG_REQUIRE(np * (uint64_t)K < 0xFFFFFFF0ull, ISG_ERR_OVERFLOW, "volume too large for 32-bit (voxel, layer) ids");
     cudaStream_t st = (cudaStream_t)stream;
     Carver cv(workspace, workspace_bytes);
     DogBuffers b;
-    dog_carve(&b, cv, np, max_seeds);
+    dog_carve(&b, cv, np, max_seeds, K);
     ISG_REQUIRE(workspace && cv.ok, ISG_ERR_WORKSPACE, "isg_dog_blob_segment: workspace too small (%zu < %zu)",
                 workspace_bytes, cv.off);
     const int grid = num_sms() * 8;
     GaussW g[4];
     for (int k = 0; k < 4; ++k) {
-        g[k].r = prm->radius[k];
-        for (int i = 0; i <= prm->radius[k]; ++i) g[k].w[i] = prm->weights[k][i];
+        if (K > 1 && k < 2) {
+            g[k].r = prm->mask_radius[k];
+            for (int i = 0; i <= g[k].r; ++i) g[k].w[i] = prm->mask_weights[k][i];
+        } else {
+            g[k].r = K > 1 ? 0 : prm->radius[k];
+            for (int i = 0; i <= g[k].r; ++i) g[k].w[i] = prm->weights[k][i];
+        }
     }
     ISG_CUDA(cudaMemsetAsync(b.scal, 0, 64 * sizeof(uint32_t), st));
     pad_kernel<<<grid, 256, 0, st>>>(vol, b.vp, (uint32_t)z, (uint32_t)y, (uint32_t)x);
@@ -320,17 +477,40 @@ extern "C" int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int6
     if ((rc = gauss3(b.vp, b.gc, b.gb, Z, Y, X, g[1], 0, st))) return rc;
     dog_combine_kernel<<<grid, 256, 0, st>>>(b.ga, b.gb, prm->threshold, mask_out, np);
     ISG_LAUNCHED();
-    // ---- blob_dog: one DoG layer of 'reflect' Gaussians, scaled, 3x3x3 maxima ---------------------
-    if ((rc = gauss3(b.vp, b.gc, b.ga, Z, Y, X, g[2], 1, st))) return rc;
-    if ((rc = gauss3(b.vp, b.gc, b.gb, Z, Y, X, g[3], 1, st))) return rc;
-    dog_cube_kernel<<<grid, 256, 0, st>>>(b.ga, b.gb, prm->scale_factor, b.gc, np);
-    ISG_LAUNCHED();
-    dog_peak_kernel<<<grid, 256, 0, st>>>(b.gc, Z, Y, X, prm->threshold, b.cand_a, (uint32_t)max_seeds,
-                                          b.scal + 0, b.scal + 1);
-    ISG_LAUNCHED();
-    uint32_t n_cand = 0;
-    ISG_CUDA(cudaMemcpyAsync(&n_cand, b.scal + 0, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    ISG_CUDA(cudaStreamSynchronize(st));
+    // ---- blob_dog: DoG layers of 'reflect' Gaussians, scaled, local maxima over space (and scale) ------
+    if (K == 1) {
+        if ((rc = gauss3(b.vp, b.gc, b.ga, Z, Y, X, g[2], 1, st))) return rc;
+        if ((rc = gauss3(b.vp, b.gc, b.gb, Z, Y, X, g[3], 1, st))) return rc;
+        dog_cube_kernel<<<grid, 256, 0, st>>>(b.ga, b.gb, prm->scale_factor, b.gc, np);
+        ISG_LAUNCHED();
+        dog_peak_kernel<<<grid, 256, 0, st>>>(b.gc, Z, Y, X, prm->threshold, b.cand_a, (uint32_t)max_seeds,
+                                              b.scal + 0, b.scal + 1);
+        ISG_LAUNCHED();
+    } else {
+        float *prev = b.ga, *cur = b.gb;
+        for (int i = 0; i <= K; ++i) {
+            GaussW gl;
+            gl.r = prm->layer_radius[i];
+            for (int j = 0; j <= gl.r; ++j) gl.w[j] = prm->layer_weights[i][j];
+            if ((rc = gauss3(b.vp, b.gc, cur, Z, Y, X, gl, 1, st))) return rc;
+            if (i > 0) {
+                dog_cube_kernel<<<grid, 256, 0, st>>>(prev, cur, prm->scale_factor, b.cube + (uint64_t)(i - 1) * np, np);
+                ISG_LAUNCHED();
+            }
+            float *t = prev; prev = cur; cur = t;
+        }
+        dog_peak4_kernel<<<grid, 256, 0, st>>>(b.cube, K, Z, Y, X, prm->threshold, b.cand_a, (uint32_t)max_seeds,
+                                               b.scal + 0, b.scal + 1, b.scal + 4);
+        ISG_LAUNCHED();
+    }
+    uint32_t n_cand = 0, max_layer = 0;
+    {
+        uint32_t head[5] = {0, 0, 0, 0, 0};
+        ISG_CUDA(cudaMemcpyAsync(head, b.scal, sizeof(head), cudaMemcpyDeviceToHost, st));
+        ISG_CUDA(cudaStreamSynchronize(st));
+        n_cand = head[0];
+        max_layer = head[4];
+    }
     ISG_REQUIRE(n_cand <= (uint64_t)max_seeds, ISG_ERR_OVERFLOW,
                 "isg_dog_blob_segment: %u blob candidates exceed max_seeds=%lld", n_cand, (long long)max_seeds);
     const uint64_t *cand_sorted = b.cand_a;
@@ -342,12 +522,20 @@ extern "C" int isg_dog_blob_segment(const float *vol, int64_t z, int64_t y, int6
     }
     ISG_CUDA(cudaMemsetAsync(b.grid, 0, np * sizeof(uint32_t), st));
     ISG_CUDA(cudaMemsetAsync(b.centroids, 0, np, st));
-    if (n_cand > 0) {
+    if (n_cand > 0 && K == 1) {
         const int blocks = (int)((n_cand + 255) / 256);
         blob_grid_kernel<<<blocks, 256, 0, st>>>(cand_sorted, n_cand, b.scal + 1, b.grid);
         ISG_LAUNCHED();
         blob_prune_kernel<<<blocks, 256, 0, st>>>(cand_sorted, n_cand, b.scal + 1, b.grid, Z, Y, X,
                                                   prm->prune_radius, prm->prune_d2, b.centroids, b.scal + 2);
+        ISG_LAUNCHED();
+    } else if (n_cand > 0) {
+        ISG_CUDA(cudaMemcpyAsync(b.sigmas, prm->layer_sigma, sizeof(double) * ISG_DOG_MAX_SIGMAS,
+                                 cudaMemcpyHostToDevice, st));
+        // _prune_blobs: distance = 2 * sigma_max * sqrt(ndim), sigma_max over the DETECTED blobs
+        const double dist = 2.0 * prm->layer_sigma[max_layer] * sqrt(3.0);
+        blob_prune_multi_kernel<<<1, 1024, 0, st>>>(cand_sorted, n_cand, K, b.scal + 1, Y, X, b.sigmas, dist,
+                                                    prm->overlap, b.sig, b.centroids, b.scal + 2);
         ISG_LAUNCHED();
     }
     // ---- exact EDT of (v != 0) ----------------------------------------------------------------------

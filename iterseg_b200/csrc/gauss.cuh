@@ -9,13 +9,13 @@
 namespace isg {
 
 struct GaussW {
-    double w[12];
+    double w[28];
     int r;
 };
 
 static constexpr int GAUSS_TL = 32;      // outputs along the filtered axis per tile
 static constexpr int GAUSS_TI = 32;      // contiguous elements per tile row
-static constexpr int GAUSS_RMAX = 11;
+static constexpr int GAUSS_RMAX = 27;     // sigma <= 6.8 at truncate = 4 (multi-layer blob_dog: sigma_list grows by 1.6x per layer)
 
 __device__ __forceinline__ int gauss_src_index(int i, int len, int reflect) {
     if (reflect) {

@@ -449,7 +449,8 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
         bool took = false;
         for (long kb : {flat_kb, 28L, 24L, 20L}) {
             if (kb > flat_kb) continue;
-            if (place(true, kb * 1024) && g.flat && !t.fold && g.T == rect.T && g.nsets == rect.nsets &&
+            const bool relax = getenv("ISG_CONV_FLAT_RELAX") != nullptr;      // experiment: accept fewer planes per group
+            if (place(true, kb * 1024) && g.flat && !t.fold && (g.T == rect.T || (relax && g.T >= 3)) && g.nsets == rect.nsets &&
                 g.b_resident == rect.b_resident && g.taps_per_b == rect.taps_per_b &&
                 g.n_b_stages >= rect.n_b_stages - 1) {
                 took = true;

@@ -458,17 +458,30 @@ def dog_blob_watershed_prep_config(input_volume_layer, unet_or_config_file, refe
 
 
 def _dog_params(min_sigma, max_sigma, threshold, sigma_ratio=1.6, overlap=0.5):
+    """isg_dog_params for blob_dog(min_sigma, max_sigma, threshold) with scikit-image's defaults
+    (sigma_ratio 1.6, overlap 0.5, exclude_border False): k = int(log(max/min)/log(ratio) + 1) DoG
+    layers from the sigma list min_sigma * ratio^i, i = 0..k (segmentation.py:637-638)."""
     import math
     if not (np.isscalar(min_sigma) and np.isscalar(max_sigma)):
         raise NotImplementedError('only scalar min_sigma / max_sigma are supported')
     k = int(math.log(float(max_sigma) / float(min_sigma)) / math.log(sigma_ratio) + 1)
-    if k != 1:
-        raise NotImplementedError(f'blob_dog with {k} DoG layers (max_sigma / min_sigma >= {sigma_ratio}) '
-                                  f'is not implemented: only the single-layer case of the default configuration')
-    s0, s1 = float(min_sigma), float(min_sigma) * sigma_ratio
+    if k < 1:
+        raise ValueError('max_sigma must not be smaller than min_sigma')
+    if k + 1 > _lib.DOG_MAX_SIGMAS:
+        raise NotImplementedError(f'blob_dog with {k} DoG layers: at most {_lib.DOG_MAX_SIGMAS - 1} are supported')
+    sl = [float(min_sigma) * sigma_ratio ** i for i in range(k + 1)]
     p = _lib.DogParams()
-    for i, sg in enumerate((float(min_sigma), float(max_sigma), s0, s1)):
+    for i, sg in enumerate((float(min_sigma), float(max_sigma), sl[0], sl[1])):
         w, r = ws.gaussian_half_kernel(sg)
+        if k > 1:
+            if i >= 2:
+                continue
+            if r > _lib.GAUSS_MAX_RADIUS:
+                raise ValueError(f'sigma {sg} needs a Gaussian radius of {r} > {_lib.GAUSS_MAX_RADIUS}')
+            p.mask_radius[i] = r
+            for j in range(r + 1):
+                p.mask_weights[i][j] = float(w[j])
+            continue
         if r > 11:
             raise ValueError(f'sigma {sg} needs a Gaussian radius of {r} > 11')
         p.radius[i] = r
@@ -476,8 +489,9 @@ def _dog_params(min_sigma, max_sigma, threshold, sigma_ratio=1.6, overlap=0.5):
             p.weights[i][j] = float(w[j])
     p.threshold = float(threshold)
     p.scale_factor = float(np.float32(1.0 / (sigma_ratio - 1)))
-    # _prune_blobs: spheres of radius sigma * sqrt(3); blobs closer than this overlap by > `overlap`
-    r = s0 * math.sqrt(3)
+    # _prune_blobs with ONE common sigma: spheres of radius sigma * sqrt(3); blobs closer than this
+    # overlap by > `overlap`
+    r = sl[0] * math.sqrt(3)
     d2max = 0
     for d2 in range(1, int((2 * r) ** 2) + 2):
         d = math.sqrt(d2)
@@ -488,6 +502,17 @@ def _dog_params(min_sigma, max_sigma, threshold, sigma_ratio=1.6, overlap=0.5):
             d2max = d2
     p.prune_d2 = d2max
     p.prune_radius = int(math.isqrt(d2max)) if d2max else 0
+    p.n_layers = k
+    p.overlap = float(overlap)
+    if k > 1:
+        for i, sg in enumerate(sl):
+            w, r = ws.gaussian_half_kernel(sg)
+            if r > _lib.GAUSS_MAX_RADIUS:
+                raise ValueError(f'sigma {sg:.3f} (layer {i}) needs a Gaussian radius of {r} > {_lib.GAUSS_MAX_RADIUS}')
+            p.layer_sigma[i] = sg
+            p.layer_radius[i] = r
+            for j in range(r + 1):
+                p.layer_weights[i][j] = float(w[j])
     return p
 
 
@@ -504,8 +529,8 @@ def dog_blob_segment_device(frame, labels, min_sigma=1, max_sigma=1.5, threshold
     if max_seeds is None:
         max_seeds = max(1 << 16, (Z * Y * X) // 8)
     p = _dog_params(min_sigma, max_sigma, threshold)
-    nbytes = lib.isg_dog_workspace_bytes(Z, Y, X, max_seeds)
-    wsb = ws._workspace('dog', (Z, Y, X, max_seeds), nbytes, dev)
+    nbytes = lib.isg_dog_workspace_bytes_layers(Z, Y, X, max_seeds, int(p.n_layers))
+    wsb = ws._workspace('dog', (Z, Y, X, max_seeds, int(p.n_layers)), nbytes, dev)
     mask = torch.empty(shape_p, dtype=torch.uint8, device=dev)
     counts = torch.zeros(4, dtype=torch.int64, device=dev)
     import ctypes

@@ -75,7 +75,33 @@ def test_dog_through_the_plugin(tmp_path):
         assert labels[t].max() > 5
 
 
-def test_dog_multi_layer_is_refused():
+@pytest.mark.parametrize('shape,seed,kw', [
+    ((12, 96, 96), 11, {'min_sigma': 1, 'max_sigma': 2, 'threshold': 0.02}),          # 2 DoG layers
+    ((16, 128, 128), 12, {'min_sigma': 1, 'max_sigma': 3, 'threshold': 0.01}),        # 3 layers, radius up to 16
+    ((33, 160, 160), 13, {'min_sigma': 0.8, 'max_sigma': 4, 'threshold': 0.02}),      # 4 layers
+])
+def test_dog_multi_layer_equals_oracle(shape, seed, kw):
+    """blob_dog with several DoG layers (max_sigma / min_sigma >= 1.6; segmentation.py:637-638 leaves the
+    sigmas to the config file): 3^4 maxima over (z, y, x, layer) and _prune_blobs with per-blob sigma,
+    against the scipy restatement (parity unpinned w.r.t. scikit-image: the pair order of the prune
+    and the heap tie rule are ours, oracle/dog.py)."""
+    from iterseg_b200 import synth
+    from oracle import dog
+    vol = synth.platelet_frame(shape, seed=seed)
+    want = np.zeros(tuple(s + 2 for s in shape), np.int32)
+    info = dog.dog_blob_watershed_for_chunks(vol, want, **kw)
+    lab, mask, dist, counts = _run_gpu(vol, **kw)
+    assert len(dog.sigma_list(kw['min_sigma'], kw['max_sigma'])) >= 3
+    assert np.array_equal(mask, info['mask'])
+    assert int(counts[1]) == len(info['blobs'])
+    assert len(np.unique(info['blobs'][:, 3])) >= 2                # blobs of different scales survive
+    assert np.array_equal(lab, want)
+    assert want.max() > 10
+
+
+def test_dog_too_many_layers_are_refused():
     from iterseg_b200 import segmentation
     with pytest.raises(NotImplementedError):
-        segmentation._dog_params(1.0, 3.0, 0.02)
+        segmentation._dog_params(0.5, 60.0, 0.02)
+    with pytest.raises(ValueError):
+        segmentation._dog_params(1.0, 20.0, 0.02)       # a layer's Gaussian radius exceeds the kernel's limit
