@@ -625,6 +625,24 @@ def run_gpu(args, rank, local_rank, world):
         p1.record()
         torch.cuda.synchronize()
         post_ms = p0.elapsed_time(p1) / reps
+        # the ordered flood alone (isg_affinity_flood on the same affinities / kept mask / kept seeds; it
+        # repeats the component labelling of its domain, ~0.15 ms): what is left is the streaming part
+        seeds_k, counts_k, mask_k, _ = ws.segment_features_device(feats, labels.zero_())
+        n_k = int(counts_k[0].item())
+        div = feats[0:3].amax(dim=(1, 2, 3)).contiguous()
+        lab2 = torch.zeros_like(labels)
+        seeds_c = seeds_k[:n_k].contiguous()
+        ws._run_flood(feats, 1, div, mask_k, seeds_c, lab2, shape_p, None)
+        torch.cuda.synchronize()
+        flood_same = bool(torch.equal(lab2, labels))
+        p0.record()
+        for _ in range(reps):
+            lab2.zero_()
+            ws._run_flood(feats, 1, div, mask_k, seeds_c, lab2, shape_p, None)
+        p1.record()
+        torch.cuda.synchronize()
+        flood_ms = p0.elapsed_time(p1) / reps
+        del lab2
     feats_host = feats.cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     # ---- configs[2] / configs[3] records ----------------------------------------------------------
@@ -705,6 +723,16 @@ def run_gpu(args, rank, local_rank, world):
             'frac': post_bytes / (post_ms * 1e-3) / 1e9 / hbm, 'traffic': None,
             'kernel': 'post-U-Net stage (seeds, Otsu mask, components, ordered flood), timed alone',
             'ms': post_ms,
+            'split': {
+                'ordered_flood_ms': flood_ms,
+                'ordered_flood': {'bytes_per_padded_voxel': 17, 'achieved_gbs': 17.0 * float(np.prod(shape_p)) / (flood_ms * 1e-3) / 1e9,
+                                  'frac': 17.0 * float(np.prod(shape_p)) / (flood_ms * 1e-3) / 1e9 / hbm,
+                                  'equals_full_post_labels': flood_same},
+                'streaming_ms': max(post_ms - flood_ms, 0.0),
+                'streaming': {'bytes_per_voxel': 14, 'achieved_gbs': 14.0 * nvox / (max(post_ms - flood_ms, 1e-3) * 1e-3) / 1e9,
+                              'frac': 14.0 * nvox / (max(post_ms - flood_ms, 1e-3) * 1e-3) / 1e9 / hbm,
+                              'what': 'Gaussians (FP64, scipy pairing order), peaks, candidate sort, histogram + Otsu, '
+                                      'mask, components, size filter'}},
             'note': 'latency bound, not HBM bound: the order-exact flood of the largest multi-seed object '
                     '(one warp per object) sets the time; see profiles/r02_notes.md'}
         if series_rec is not None:
