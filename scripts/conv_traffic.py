@@ -1,12 +1,20 @@
-"""profiles/r01_conv_traffic.json from an `ncu --set full` raw page of the tensor-core convolutions.
+"""profiles/r02_conv_traffic.json from an `ncu --set full` raw page of one U-Net forward.
 
-    ncu --set full --clock-control none -k regex:'conv3d_tc|conv3d_zring' -c 16 -o rep python scripts/time_unet.py
+    ncu --set full --clock-control none -k regex:'conv3d|conv_in|conv_out|bn_relu|place_kernel' -s 70 -c 35 -o rep \
+        python scripts/time_unet.py
     ncu -i rep.ncu-rep --page raw --csv > raw.csv
-    python scripts/conv_traffic.py raw.csv profiles/r01_conv_traffic.json
+    python scripts/conv_traffic.py raw.csv profiles/r02_conv_traffic.json
+
+The file carries the kernel label bench.py prints (`TC_KERNEL_LABEL`): bench.py uses the traffic figure
+only when the two agree, so a capture of an older kernel set can never be quoted for a newer binary.
 """
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench      # noqa: E402  (TC_KERNEL_LABEL)
 
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -39,7 +47,7 @@ for r in data:
 layers = layers[:16]
 out = {
     'source': f'{sys.argv[1]} (ncu --set full, scripts/time_unet.py, one frame = 36 chunks)',
-    'kernel': 'conv3d_tc_kernel + conv3d_zring32_kernel + conv3d_zring_kernel',
+    'kernel_label': bench.TC_KERNEL_LABEL,
     'launches': len(layers),
     'dram_bytes_per_launch': sum((l['dram_r_gb'] + l['dram_w_gb']) * 1e9 for l in layers) / max(len(layers), 1),
     'layers': layers,
