@@ -904,7 +904,8 @@ def main():
     ap.add_argument('--no-slab-check', action='store_true',
                     help='skip the single-device run the slab labels are compared with')
     ap.add_argument('--slab-shape', type=int, nargs=3, default=[256, 2048, 2048])
-    ap.add_argument('--slab-halo', type=int, default=24)
+    ap.add_argument('--slab-halo', type=int, default=32,
+                    help='halo planes per seam; the guard raises it by 8 when an object does not fit (24 was refused on the bench volume at N = 4 and 8)')
     ap.add_argument('--segmenter', default='affinity', choices=['affinity', 'dog'],
                     help="'dog': the DoG blob watershed (BASELINE.json configs[4]) instead of the headline path")
     args = ap.parse_args()

@@ -1,7 +1,7 @@
 """Diagnosis: GPU features vs the fp32 oracle on the 12x300x300 structured-network frame."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from iterseg_b200 import predict, synth, unet, segmentation
 from oracle import unet_ref, post, metrics
 CHUNK, MARGIN = (10, 256, 256), (1, 64, 64)
