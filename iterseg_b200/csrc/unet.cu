@@ -172,7 +172,7 @@ struct isg_unet_plan {
     cudaEvent_t tabs_ev;          // recorded after an upload: the pinned copy may be rewritten once it is done
     int tabs_ev_pending;
     __half *raw[5], *act[5], *skip[4], *pooled[5], *up[4];
-    float *raw8, *raw9;
+    __half *raw8, *raw9;          // the two 5-channel layers: fp16 [vox][8] (16 bytes per voxel)
     unsigned long long *stats[18];
     unsigned long long *stats_all;
     unsigned int *sched[18];
@@ -243,8 +243,8 @@ static size_t plan_carve(isg_unet_plan *p, Carver &cv) {
         if (l > 0) p->pooled[l] = cv.take<__half>(vox(l) * CH[l - 1]);
         else p->pooled[l] = nullptr;
     }
-    p->raw8 = cv.take<float>(vox(0) * 8);
-    p->raw9 = cv.take<float>(vox(0) * 8);
+    p->raw8 = cv.take<__half>(vox(0) * 8);
+    p->raw9 = cv.take<__half>(vox(0) * 8);
     size_t floats = 0;
     for (int i = 0; i < 18; ++i) floats += (size_t)N * cout_pad(i) * 2;
     // + one 8-byte slot per conv for the group counter of its dynamic scheduler (unet_conv.cuh);
@@ -312,7 +312,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
         z.tiles_w = (z.W + ZR_WT - 1) / ZR_WT;
         z.tiles_h = (z.H + ZR_HT - 1) / ZR_HT;
         z.n_cols = z.N * z.tiles_h * z.tiles_w;
-        z.out = reinterpret_cast<float *>(out);
+        z.out = reinterpret_cast<__half *>(out);
         z.stats = p->stats[i];
         z.sched = p->sched[i];
         t.zring = 1;
@@ -1051,8 +1051,8 @@ extern "C" int isg_unet_debug_activation(isg_unet_plan *plan, const float *frame
     ISG_REQUIRE((int64_t)(vox * C) == out_elems, ISG_ERR_ARG, "out must hold %zu floats", vox * C);
     const void *src;
     int is_f32 = 0, cstride = cout_pad(idx);
-    if (idx == 16) { src = plan->raw8 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
-    else if (idx == 17) { src = plan->raw9 + (size_t)chunk * vox * 8; is_f32 = 1; cstride = 8; }
+    if (idx == 16) { src = plan->raw8 + (size_t)chunk * vox * 8; cstride = 8; }
+    else if (idx == 17) { src = plan->raw9 + (size_t)chunk * vox * 8; cstride = 8; }
     else src = plan->raw[l] + (size_t)chunk * vox * cstride;
     debug_to_ncdhw_kernel<<<num_sms() * 4, 256, 0, st>>>(
         src, is_f32, cstride, C, vox, reinterpret_cast<const float *>(plan->packed + plan->L.inv_s[idx]), out);

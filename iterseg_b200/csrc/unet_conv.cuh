@@ -74,7 +74,7 @@ struct ConvGeom {
     int n_b_stages;
     int taps_per_b;              // taps per B stage (template parameter G): 1, 3 or 9
     int b_resident;              // 1: all (nkb x 27/G) weight stages are loaded once and kept
-    int out_mode;                // 0: fp16 [vox][cout]   1: fp32 [vox][8] (first 8 columns)
+    int out_mode;                // 0: fp16 [vox][cout]   1: fp16 [vox][8] (first 8 columns)
     int debug;                   // ISG_CONV_DEBUG (diagnosis only): 1 skip epilogue body, 2 skip A loads, 4 skip B loads
     void *out;
     unsigned long long *stats;   // [N][cout][2] (sum, sum of squares) as 2^-24 fixed point:
@@ -522,11 +522,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     tmem_ld_wait();
                 }
                 if (valid) {
-                    float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + vox * 8);
-                    o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
-                                       __uint_as_float(v[2]), __uint_as_float(v[3]));
-                    o[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
-                                       __uint_as_float(v[6]), __uint_as_float(v[7]));
+                    uint4 pk;
+                    __half2 *h2 = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        h2[e] = __floats2half2_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(g.out) + vox * 8) = pk;
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) st[lane * 33 + j] = valid ? __uint_as_float(v[j]) : 0.0f;

@@ -249,7 +249,7 @@ bn_relu_up_kernel(const __half *__restrict__ raw, __half *__restrict__ up,
 // sigmoid(bn(raw9)) -> the cropped interior of every chunk is placed into the
 // (5, Z, Y, X) feature volume (predict.py:89-95): each voxel is written by exactly one chunk.
 __global__ void __launch_bounds__(256)
-place_kernel(const float *__restrict__ raw9, const unsigned long long *__restrict__ stats9,
+place_kernel(const __half *__restrict__ raw9, const unsigned long long *__restrict__ stats9,
              const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ eps,
              const int *__restrict__ starts, const int *__restrict__ crop_lo,
              const int *__restrict__ crop_hi, float *__restrict__ feats, int Z, int Y, int X, int D,
@@ -272,10 +272,11 @@ place_kernel(const float *__restrict__ raw9, const unsigned long long *__restric
         const size_t t = i / cw;
         const int h = ly + (int)(t % ch);
         const int d = lz + (int)(t / ch);
-        const float4 *p = reinterpret_cast<const float4 *>(
-            raw9 + ((size_t)n * vox + ((size_t)d * H + h) * W + w) * 8);
-        const float4 lo = __ldg(p), hi = __ldg(p + 1);
-        const float x[5] = {lo.x, lo.y, lo.z, lo.w, hi.x};
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(
+            raw9 + ((size_t)n * vox + ((size_t)d * H + h) * W + w) * 8));
+        const __half2 *hh = reinterpret_cast<const __half2 *>(&u);
+        const float2 a01 = __half22float2(hh[0]), a23 = __half22float2(hh[1]), a45 = __half22float2(hh[2]);
+        const float x[5] = {a01.x, a01.y, a23.x, a23.y, a45.x};
         const size_t o = ((size_t)(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {

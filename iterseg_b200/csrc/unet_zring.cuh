@@ -33,7 +33,7 @@ struct ZringGeom {
     int N, D, H, W;              // chunks, chunk extents
     int tiles_w, tiles_h;
     int n_cols;                  // N * tiles_h * tiles_w z-columns
-    float *out;                  // fp32 [N][vox][8]
+    __half *out;                 // fp16 [N][vox][8] raw (pre-BatchNorm) output: one 16-byte store per voxel
     unsigned long long *stats;   // [N][16][2] fixed point (see unet_conv.cuh)
     unsigned int *sched;         // column counter, zeroed by the caller
 };
@@ -156,9 +156,11 @@ __device__ __forceinline__ void zring_epilogue(const ZringGeom &g, uint32_t tmem
             for (int j = 0; j < 8; ++j)
                 o[j] = S[0][j] + __shfl_down_sync(0xFFFFFFFFu, S[1][j], 1) + __shfl_down_sync(0xFFFFFFFFu, S[2][j], 2);
             if (valid) {
-                float4 *dst = reinterpret_cast<float4 *>(g.out + ((size_t)n * vox_chunk + ((size_t)z * g.H + h) * g.W + w) * 8);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                uint4 pk;
+                __half2 *h2 = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                *reinterpret_cast<uint4 *>(g.out + ((size_t)n * vox_chunk + ((size_t)z * g.H + h) * g.W + w) * 8) = pk;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) st[lane * 9 + j] = valid ? o[j] : 0.0f;
@@ -358,8 +360,8 @@ static constexpr int ZO_SLOTS = 3;
 static constexpr int ZO_THREADS = 288;
 
 struct ZoutArgs {
-    ZringGeom g;                          // out = raw9 fp32 [N][vox][8], stats = stats9 [N][5][2]
-    const float *src;                     // raw8 fp32 [N][vox][8]
+    ZringGeom g;                          // out = raw9 fp16 [N][vox][8], stats = stats9 [N][5][2]
+    const __half *src;                    // raw8 fp16 [N][vox][8]
     const unsigned long long *stats_in;   // [N][16][2]
     const float *gamma_in, *beta_in, *eps_in;
     const float *wgt;                     // [27][5 in][5 out] fp32
@@ -472,21 +474,27 @@ conv_out_zring_kernel(const ZoutArgs a) {
             const int h1 = hb * ZR_HT - 1 + (r1 >> 5), w1 = wb * ZR_WT - 1 + (r1 & 31);
             const bool in0 = h0 >= 0 && h0 < H && w0 >= 0 && w0 < W;
             const bool in1 = has1 && h1 >= 0 && h1 < H && w1 >= 0 && w1 < W;
-            const float *p0 = a.src + ((size_t)n * vox_chunk + (size_t)(in0 ? h0 : 0) * W + (in0 ? w0 : 0)) * 8;
-            const float *p1 = a.src + ((size_t)n * vox_chunk + (size_t)(in1 ? h1 : 0) * W + (in1 ? w1 : 0)) * 8;
+            const __half *p0 = a.src + ((size_t)n * vox_chunk + (size_t)(in0 ? h0 : 0) * W + (in0 ? w0 : 0)) * 8;
+            const __half *p1 = a.src + ((size_t)n * vox_chunk + (size_t)(in1 ? h1 : 0) * W + (in1 ? w1 : 0)) * 8;
             const size_t zstride = (size_t)H * W * 8;
             float4 c0lo, c1lo;
             float c0hi, c1hi;
             auto load = [&](int p, float4 &lo0, float &hi0, float4 &lo1, float &hi1) {
                 lo0 = lo1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 hi0 = hi1 = 0.f;
-                if (in0) {
-                    lo0 = __ldg(reinterpret_cast<const float4 *>(p0 + p * zstride));
-                    hi0 = __ldg(p0 + p * zstride + 4);
+                if (in0) {                                        // one 16-byte load per voxel: 8 halves, 5 used
+                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p0 + p * zstride));
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                    const float2 a01 = __half22float2(h[0]), a23 = __half22float2(h[1]), a45 = __half22float2(h[2]);
+                    lo0 = make_float4(a01.x, a01.y, a23.x, a23.y);
+                    hi0 = a45.x;
                 }
                 if (in1) {
-                    lo1 = __ldg(reinterpret_cast<const float4 *>(p1 + p * zstride));
-                    hi1 = __ldg(p1 + p * zstride + 4);
+                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p1 + p * zstride));
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                    const float2 a01 = __half22float2(h[0]), a23 = __half22float2(h[1]), a45 = __half22float2(h[2]);
+                    lo1 = make_float4(a01.x, a01.y, a23.x, a23.y);
+                    hi1 = a45.x;
                 }
             };
             auto pack = [&](const float4 &lo, float hi, bool in) {
