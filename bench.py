@@ -162,12 +162,17 @@ def cpu_full_frame(vol, sd, threads):
     return time.perf_counter() - t0, t_unet, t_post, lab
 
 
+REF_WHOLE_FRAME_BUDGET_S = 200.0       # whole-frame steps until this much time is spent, then bounded samples
+
+
 def run_reference(args, rank):
     """The reference's CPU path on this box's host cores: every timed step is ONE WHOLE FRAME -- all 36
     chunks through the fp32 torch-CPU U-Net with every host thread, crop-and-place, the scipy/numpy
     seeds / mask / components stage and the single-threaded heap flood on that network-derived
-    feature volume.  Nothing is extrapolated unless the run would exceed ~5 minutes (then the
-    remaining steps time 2 of the 36 chunks + the whole post stage and say so)."""
+    feature volume (~13 s on a 16-core host).  Whole frames are measured until REF_WHOLE_FRAME_BUDGET_S
+    are spent; if K steps do not fit (the driver's K = 20 would need 4.5 minutes), the remaining steps
+    time a bounded sample -- 2 of the 36 chunks, extrapolated, plus the measured post-stage time -- and
+    the line says how many steps were whole frames."""
     if rank != 0:
         return 0
     from iterseg_b200 import synth
@@ -186,7 +191,7 @@ def run_reference(args, rank):
     for k in range(args.steps):
         spent = time.perf_counter() - t_begin
         est = (spent / k) if k else 0.0
-        if k == 0 or spent + est * (args.steps - k) <= 300.0:
+        if k == 0 or spent + est <= REF_WHOLE_FRAME_BUDGET_S:
             dt, t_unet, t_post, _ = cpu_full_frame(vol, sd, threads)
             times.append(dt)
             splits.append((t_unet / n_chunks, t_post))
@@ -212,7 +217,8 @@ def run_reference(args, rank):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'frame': list(FRAME), 'chunk': list(CHUNK), 'margin': list(MARGIN)},
         'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                         'sample': sample, 'extrapolated': extrapolated,
+                         'sample': sample, 'extrapolated': extrapolated, 'whole_frame_steps': n_full,
+                         'whole_frame_mean_s': float(np.mean(times[:n_full])),
                          'step_s': [round(t, 2) for t in times]},
         'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
