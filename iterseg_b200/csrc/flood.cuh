@@ -285,6 +285,12 @@ static constexpr uint32_t BQ_SMEM_L = 232448;        // 1 per SM (227 KB)
 static constexpr uint32_t BQ_SEED_FLAG = 0x80000000u;
 static constexpr uint32_t BQ_MAX_POS = 65535u;       // positions and node ids are 16-bit
 static constexpr uint32_t BQ_HEADER = 1024u + 128u;  // 32 record staging slots + refill scratch
+#ifndef BQ_SWEEP
+#define BQ_SWEEP true                                // the dead-entry sweep of flood_bq_kernel (-DBQ_SWEEP=false: off)
+#endif
+#ifndef BQ_SWEEP_EVERY
+#define BQ_SWEEP_EVERY 4u
+#endif
 
 __host__ __device__ __forceinline__ uint32_t bq_smem_bytes(uint32_t nodes, uint32_t seeds) {
     const uint32_t P = 3u * nodes + seeds;
@@ -370,11 +376,43 @@ flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
         };
         uint32_t F = EMPTY;          // this lane's front entry
         uint32_t bmin = 0;           // every back entry is >= bmin, every front entry < bmin
+        uint32_t age = 0;            // pops since this lane requested its record (the sweep waits for age >= 3)
+        uint32_t sweep_it = 0;
+        const bool sweep_on = BQ_SWEEP;
 #ifdef FLOOD_PROF
         unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long tc0 = clock64();
 #endif
         for (;;) {
+            // ---- dead-entry sweep -------------------------------------------------------------
+            // About half of all pops claim nothing: every neighbour of the popped node has been
+            // labelled in the meantime.  Labels are only ever added, so an entry whose node has no
+            // unlabelled neighbour left stays a no-op for ever -- and a no-op pop touches neither
+            // labels nor tail counters nor positions.  Such entries are dropped HERE, by all 32 lanes at
+            // once (each lane tests the node of its own front entry against the record it has
+            // staged), instead of one by one on the ordered critical path.  The result is identical.
+            if (sweep_on) {
+                ++age;
+                // every BQ_SWEEP_EVERY-th iteration: the sweep costs ~130 clk, a dead pop ~300
+                if ((++sweep_it % BQ_SWEEP_EVERY) == 0u && F != EMPTY && age >= 3u) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    const uint4 r = *reinterpret_cast<const uint4 *>(smem_raw + lane * 32u);
+                    // branch-free: a missing neighbour reads the entry's own node, which is labelled
+                    const uint32_t self = F & 0xFFFFu;
+                    uint32_t n0 = r.x & 0xFFFFu, n1 = r.x >> 16, n2 = r.y & 0xFFFFu, n3 = r.y >> 16,
+                             n4 = r.z & 0xFFFFu, n5 = r.z >> 16;
+                    n0 = n0 == NO_NODE ? self : n0;
+                    n1 = n1 == NO_NODE ? self : n1;
+                    n2 = n2 == NO_NODE ? self : n2;
+                    n3 = n3 == NO_NODE ? self : n3;
+                    n4 = n4 == NO_NODE ? self : n4;
+                    n5 = n5 == NO_NODE ? self : n5;
+                    const uint32_t l0 = slab[n0], l1 = slab[n1], l2 = slab[n2], l3 = slab[n3], l4 = slab[n4],
+                                   l5 = slab[n5];
+                    const bool dead = (l0 != 0) & (l1 != 0) & (l2 != 0) & (l3 != 0) & (l4 != 0) & (l5 != 0);
+                    F = dead ? EMPTY : F;
+                }
+            }
             uint32_t mn = __reduce_min_sync(FULL, F);
             if (mn == EMPTY) {
                 // ---- refill the front from the back: the first non-empty word and the 31 after it ----
@@ -414,6 +452,7 @@ flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
                     const uint32_t node = slots[pos];
                     F = (pos << 16) | node;
                     request(node);
+                    age = 0;
                 }
                 bmin = (i1 + kk) * 32u;
                 __syncwarp();
@@ -471,6 +510,7 @@ flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
                     if (lane == (unsigned)__ffs((int)free_lanes) - 1u) {
                         F = xs;
                         request(xs & 0xFFFFu);
+                        age = 0;
                     }
                 } else {
                     // front full: the larger of (new entry, front maximum) moves to the back
@@ -480,6 +520,7 @@ flood_bq_kernel(FloodWork w, BqGraph g, uint32_t *cursor, uint32_t *labels) {
                     if (mx > xs && F == mx) {
                         F = xs;
                         request(xs & 0xFFFFu);
+                        age = 0;
                     }
                     if (lane == 0) back_insert(y >> 16);
                     bmin = y >> 16;

@@ -45,4 +45,4 @@ if hasattr(lib, 'isg_debug_flood_prof'):
     v = list(buf)
     pops = max(v[0], 1)
     print(f'bucket-queue flood, comps > 5000 nodes: pops {v[0]}  clk/pop {v[6]/pops:.0f}; per pop: refills {v[1]/pops:.3f} '
-          f'front pushes {v[2]/pops:.2f} back pushes {v[3]/pops:.2f} evictions {v[4]/pops:.4f}')
+          f'front pushes {v[2]/pops:.2f} back pushes {v[3]/pops:.2f} evictions {v[4]/pops:.4f} swept {v[5]/pops:.3f}')
