@@ -537,7 +537,8 @@ def run_gpu(args, rank, local_rank, world):
     n_e2e = max(8 * args.steps, 64)             # long enough that pipeline fill / drain (~1 frame) is amortised
     series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
     out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
-    config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False}
+    config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False,
+              'global_label_offsets': world > 1}
 
     def run_e2e(out=None):
         out = out_series.numpy() if out is None else out

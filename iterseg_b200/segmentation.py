@@ -285,8 +285,12 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
     want_offsets = bool(config.get('global_label_offsets'))
     if want_offsets and kind != 'affinity':
         raise NotImplementedError('global_label_offsets is implemented for the affinity U-Net watershed only')
-    n_steps = (int(data.shape[0]) + world - 1) // world        # lock-step count when offsets are global
-    offsets = idist.LabelOffsets(rank, world, dev, config.get('process_group')) if want_offsets else None
+    # global label ids: one all-gather per step over ALL ranks of the job, sharded (step s = frames
+    # sR..sR+R-1) or not (every rank runs its own copy of the loop, e.g. one series per rank: step s =
+    # frame s of every rank); every rank must take the same number of steps
+    o_rank, o_world = idist.world(config.get('process_group')) if want_offsets else (0, 1)
+    n_steps = (int(data.shape[0]) + world - 1) // world if world > 1 else int(data.shape[0])
+    offsets = idist.LabelOffsets(o_rank, o_world, dev, config.get('process_group')) if want_offsets else None
 
     depth = int(os.environ.get('ISG_PIPE_DEPTH', '2')) if kind == 'affinity' else 2   # U-Nets submitted ahead of the post stage
 
