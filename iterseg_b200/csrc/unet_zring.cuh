@@ -58,7 +58,7 @@ __host__ __device__ constexpr size_t zring_smem_bytes() {
 
 // Epilogue of the z-ring kernels (4 warps, warp ew = TMEM lanes 32*ew.. = patch row ew): walks the
 // columns published by the scheduler; output plane z = sum over the input planes z-1, z, z+1 of
-// their (dz, dx) column blocks, dx by warp shuffle; fp32 [vox][8] store + BatchNorm sums.
+// their (dz, dx) column blocks, dx by warp shuffle; fp16 [vox][8] store + BatchNorm sums (of the fp32 values).
 // NA accumulators of ZR_N columns in the ring; statistics laid out [N][SSTRIDE][2].
 template <int NA, int SSTRIDE, bool BATCH_LD>
 __device__ __forceinline__ void zring_epilogue(const ZringGeom &g, uint32_t tmem_base, uint64_t *acc_full,
@@ -347,7 +347,7 @@ conv3d_zring_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 // per frame).  Here the input is K = 16 (5 channels + zeros), so an input plane needs only THREE
 // MMAs (one per dy; the nine (dz,dx) taps are the N = 80 columns as above).  The input cannot come
 // through TMA because BatchNorm + ReLU of c8_0.conv0's raw output sit in front of it: four producer
-// warps load the fp32 [vox][8] halo plane, normalise, convert and write the rows themselves --
+// warps load the fp16 [vox][8] halo plane, normalise, convert and write the rows themselves --
 // one 16-byte chunk per voxel at its 64-byte-swizzled position (rows are 64 bytes so that the
 // layout is the one the other kernels use; only K step 0 is ever read, its second chunk is zeroed
 // once) -- then fence.proxy.async and arrive on the plane's mbarrier.  The next plane's loads are
