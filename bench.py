@@ -571,6 +571,9 @@ def run_gpu(args, rank, local_rank, world):
     frame_done_ms = [round(e0.elapsed_time(ev), 2) for ev in step_events]     # when each frame's labels were ready
     prof = (ctypes_double_array(5))
     _lib.check(lib.isg_unet_plan_profile_read(plan.ptr, prof), 'profile_read')
+    tl = ctypes_double_array(256)
+    n_tl = lib.isg_unet_plan_profile_timeline(plan.ptr, tl, 128)
+    unet_gaps_ms = [round(tl[2 * i + 2] - tl[2 * i + 1], 3) for i in range(n_tl - 1)]     # idle between forwards
     _lib.check(lib.isg_unet_plan_profile(plan.ptr, 0), 'profile')
     tc_ms, n_tc, fw_ms, n_fw, tc_flops = [float(x) for x in prof]
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -694,7 +697,7 @@ def run_gpu(args, rank, local_rank, world):
                        'network': 'synthetic state_dict (structured carriers + dense random weights), '
                                   'fp16 operands / fp32 accumulate (bf16 misses the 1e-2 parity gate)',
                        'l2': 'inputs larger than L2: ~13.8 GB of activations streamed per step',
-                       'frame_done_ms': frame_done_ms,
+                       'frame_done_ms': frame_done_ms, 'unet_gaps_ms': unet_gaps_ms,
                        'objects': {'seeds': counts_h[0], 'components': counts_h[2],
                                    'multi_seed_components': counts_h[3]}},
             'e2e': {'value': e2e_value, 'unit': 'voxels/s',

@@ -307,6 +307,8 @@ int isg_unet_plan_profile_read(isg_unet_plan *plan, double *out);
 /* per-launch times (ms) of the recorded forward passes in launch order, 35 launches per forward;
  * kind_out (nullable): 0 = TMA-fed tcgen05 convolution, 2 = any other kernel.  Returns the count. */
 int isg_unet_plan_profile_launches(isg_unet_plan *plan, double *ms_out, int *kind_out, int cap);
+/* (start, end) of every recorded whole forward pass in ms since the first start; returns the count */
+int isg_unet_plan_profile_timeline(isg_unet_plan *plan, double *out, int cap);
 
 /* ---- label bookkeeping for frame-sharded time series ------------------------
  * labels[i] += offset for every non-zero label (global label ids across frames:

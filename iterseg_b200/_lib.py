@@ -77,6 +77,7 @@ SIGNATURES = {
     'isg_unet_plan_profile': (_i32, [_vp, _i32]),
     'isg_unet_plan_profile_read': (_i32, [_vp, _vp]),
     'isg_unet_plan_profile_launches': (_i32, [_vp, _vp, _vp, _i32]),
+    'isg_unet_plan_profile_timeline': (_i32, [_vp, _vp, _i32]),
     'isg_add_label_offset': (_i32, [_vp, _i64, _c.c_uint32, _vp]),
     'isg_crop_labels': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
 }

@@ -1016,6 +1016,25 @@ extern "C" int isg_unet_plan_profile_launches(isg_unet_plan *plan, double *ms_ou
     return n;
 }
 
+// Start / end of every recorded WHOLE forward pass in ms since the first one started (diagnosis of the
+// gaps between consecutive forward passes on a stream).  out[2i], out[2i+1]; returns the number of passes.
+extern "C" int isg_unet_plan_profile_timeline(isg_unet_plan *plan, double *out, int cap) {
+    if (!plan || !out) return 0;
+    int n = 0;
+    cudaEvent_t first = nullptr;
+    for (size_t s = 0; s + 1 < plan->ev_used && n < cap; s += 2) {
+        if (plan->ev_kind[s / 2] != 1) continue;
+        if (!first) first = plan->ev[s];
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, first, plan->ev[s]) != cudaSuccess) break;
+        if (cudaEventElapsedTime(&b, first, plan->ev[s + 1]) != cudaSuccess) break;
+        out[2 * n] = a;
+        out[2 * n + 1] = b;
+        ++n;
+    }
+    return n;
+}
+
 extern "C" double isg_unet_plan_flops(const isg_unet_plan *plan) { return plan ? plan->flops : 0.0; }
 
 extern "C" int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feats, void *stream) {
