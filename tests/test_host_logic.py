@@ -253,3 +253,26 @@ def test_series_and_volume_synth_are_rank_consistent():
     p = synth.big_volume_planes((40, 96, 96), 10, 14, tile=(8, 32, 32))
     q = synth.big_volume_planes((40, 96, 96), 0, 40, tile=(8, 32, 32))
     assert np.array_equal(p, q[10:14]) and q.min() > 0
+
+
+def test_label_store_partial_writes_in_place(tmp_path):
+    """Partial chunk updates (a frame of a multi-frame t-chunk, sub-blocks, single rows) are written in
+    place -- positional writes for contiguous runs, a shared mapping otherwise -- for every chunk shape,
+    and read back (region reads) exactly."""
+    from iterseg_b200 import _io
+    rng = np.random.default_rng(0)
+    for k, chunks in enumerate([(10, 4, 16), (4, 2, 7, 5), (3, 5, 40, 30), (1, 1, 1, 1), (25, 5, 40)]):
+        a = _io.open_zarr(str(tmp_path / f'a{k}'), shape=(25, 5, 40, 30), chunks=chunks, dtype=np.int32)
+        ref = np.zeros((25, 5, 40, 30), np.int32)
+        for t in (3, 11, 24, 0, 19):
+            v = rng.integers(1, 100, (5, 40, 30)).astype(np.int32)
+            a[t, ...] = v
+            ref[t] = v
+        a[5:7, 1:3, 7:29, 3:17] = 7
+        ref[5:7, 1:3, 7:29, 3:17] = 7
+        a[8, 2, 5] = np.arange(30)
+        ref[8, 2, 5] = np.arange(30)
+        assert np.array_equal(np.asarray(a), ref), chunks
+        assert np.array_equal(a[11], ref[11]) and np.array_equal(a[5:7, 1:3], ref[5:7, 1:3])
+        b = _io.open_zarr(str(tmp_path / f'a{k}'))                    # re-open: own metadata
+        assert np.array_equal(np.asarray(b), ref)
