@@ -1,22 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the affinity U-Net watershed path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--segmenter dog]
 
 One step = one pass of the hot path over one synthetic 33x512x512 zyx frame
 (BASELINE.json configs[1]): chunked U-Net (36 chunks of (10,256,256), margin
 (1,64,64), all batched) -> seeds / Otsu mask / components -> exact flood.
 With N > 1 (torchrun, one rank per GPU) every rank segments its own frame per
-step (frame-wise sharding, weak scaling) and the ranks all-gather their label
-counts over NCCL to make label ids global.
+step (weak scaling) and the ranks all-gather their label counts over NCCL every
+step; the running global label offset stays on the device.
 
-Printed (rank 0, one JSON line): `value` = voxels/s with the frame resident in
-HBM, device-timed with CUDA events, max over ranks; `e2e` = the same through the
-public frame loop `segmentation.segmentation_loop` (what `segment_data` runs) over a
-pinned tzyx series (H2D of every frame, D2H of its labels inside the timed region);
-`roofline` for the dominant kernel family (tcgen05 conv3d; tensor bound);
-`cpu_baseline` = the oracle port of the reference timed on this box's host
-cores on a bounded sample.  `--impl reference` times only that CPU path.
+Printed (rank 0, one JSON line):
+  value          voxels/s with the frame resident in HBM, device-timed with CUDA events, max over ranks
+  e2e            the same through the public frame loop `segmentation.segmentation_loop` (what
+                 `segment_data` runs) over a pinned tzyx series of max(8K, 64) frames: H2D of every
+                 frame and D2H of its labels inside the timed region;  e2e_zarr: the same loop
+                 writing an OME-zarr label store (`save_dir`)
+  roofline       the 16 TMA-fed tcgen05 conv launches (tensor bound), timed live with CUDA events;
+                 unet_whole_network: all 35 launches against the sustained and the burst peak
+  roofline_post  the post stage alone against the HBM copy bandwidth, split into the ordered flood
+                 and the streaming part
+  series         BASELINE.json configs[2]: ONE 192-frame series through the public loop, frames
+                 t = rank (mod N), global label ids, in memory and into ONE OME-zarr store (strong scaling)
+  slab           (N > 1) configs[3]: 256x2048x2048 in z-slabs, compared bit for bit with the
+                 single-device run of the same volume on rank 0
+  cpu_baseline   (N = 1) the oracle port of the reference on this box's host cores: one whole frame
+  config.frame_done_ms / unet_gaps_ms   when each frame's labels were ready; idle time between U-Nets
+`--impl reference` times only that CPU path (whole frames per step).
 `--segmenter dog` measures the plugin's second segmenter (configs[4]) with the same contract.
 """
 import argparse

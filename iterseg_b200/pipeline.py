@@ -126,6 +126,25 @@ class DogCore:
         return slot['labels'], slot['counts']
 
 
+# Pinned host staging buffers survive a series loop: page-locking 35 MB takes ~10 ms, which is half a
+# frame -- a second loop of the same shape (warm restart, the next series of a batch job) finds them here.
+_PINNED_POOL = {}
+_PINNED_POOL_MAX = 12
+
+
+def _pinned_take(shape, dtype):
+    lst = _PINNED_POOL.get((tuple(shape), dtype))
+    if lst:
+        return lst.pop()
+    return torch.empty(tuple(shape), dtype=dtype).pin_memory()
+
+
+def _pinned_give(t):
+    lst = _PINNED_POOL.setdefault((tuple(t.shape), t.dtype), [])
+    if len(lst) < _PINNED_POOL_MAX:
+        lst.append(t)
+
+
 class SeriesPipeline:
     """Host frames in, host labels out, several frames in flight (the frame loop of
     segmentation.py:873-882 without a host synchronisation on the compute streams):
@@ -186,6 +205,7 @@ class SeriesPipeline:
         for o in range(self.N_OUT):
             self.free_out.put(o)
         self.n_staged = 0
+        self._owned_in = []
         self.closed = False
         self.held = __import__('collections').deque()      # zero-copy: pinned buffers of the frames in flight
         torch.cuda.synchronize(self.dev)
@@ -203,7 +223,8 @@ class SeriesPipeline:
         with self._in_lock:
             if self.free_in.empty() and self._n_in_alloc < self.N_IN:
                 self._n_in_alloc += 1
-                buf = torch.empty(self.shape, dtype=torch.float32).pin_memory()
+                buf = _pinned_take(self.shape, torch.float32)
+                self._owned_in.append(buf)
         import queue
         while buf is None:                                       # never block for ever: close() wakes us up
             if self.closed:
@@ -216,7 +237,18 @@ class SeriesPipeline:
         return 'buf', buf
 
     def close(self):
+        """Wake loader threads that wait for a buffer.  Call `recycle()` once every thread is done."""
         self.closed = True
+
+    def recycle(self):
+        """Hand the pinned staging buffers back to the module-level pool (all copies must have completed)."""
+        for buf in self._owned_in:
+            _pinned_give(buf)
+        self._owned_in = []
+        for out in self.outs:
+            if out['host'] is not None:
+                _pinned_give(out['host'])
+                out['host'] = None
 
     # ---- main thread ---------------------------------------------------------------------------
     def h2d(self, loaded):
@@ -299,7 +331,7 @@ class SeriesPipeline:
                     offset_dev.record_stream(self.core.s_post)
             if dst is None:
                 if out['host'] is None:
-                    out['host'] = torch.empty(self.shape, dtype=torch.int32).pin_memory()
+                    out['host'] = _pinned_take(self.shape, torch.int32)
                 dst = out['host']
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(out['ev_post'])

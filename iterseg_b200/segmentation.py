@@ -413,9 +413,10 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
             LAST_COUNTS['global_total'] = offsets.total
     finally:
         pipe.close()                                             # wakes loader threads waiting for a buffer
-        loaders.shutdown(wait=False, cancel_futures=True)
+        loaders.shutdown(wait=True, cancel_futures=True)
         writers.shutdown(wait=True)
         torch.cuda.synchronize(dev)
+        pipe.recycle()                                           # pinned staging buffers back to the pool
 
 
 def segment_single_volume(input_volume, chunk_size, config, margin, processing_function):
