@@ -318,10 +318,12 @@ def _pipelined_series(data, chunk_size, margin, output_labels, config, frames, k
         return pipe.load(data[t])
 
     def store(t, o, host, direct):
-        pipe.outs[o]['ev_d2h'].synchronize()
-        if not direct:
-            output_labels[t, ...] = host.numpy()
-        pipe.release(o)
+        try:
+            pipe.outs[o]['ev_d2h'].synchronize()
+            if not direct:
+                output_labels[t, ...] = host.numpy()
+        finally:
+            pipe.release(o)            # also when the store raised: the main thread must never wait for this slot
         return t
 
     def direct_dst(t):
