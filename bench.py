@@ -13,7 +13,7 @@ step; the running global label offset stays on the device.
 Printed (rank 0, one JSON line):
   value          voxels/s with the frame resident in HBM, device-timed with CUDA events, max over ranks
   e2e            the same through the public frame loop `segmentation.segmentation_loop` (what
-                 `segment_data` runs) over a pinned tzyx series of max(8K, 64) frames: H2D of every
+                 `segment_data` runs) over a pinned tzyx series of 64-96 frames: H2D of every
                  frame and D2H of its labels inside the timed region;  e2e_zarr: the same loop
                  writing an OME-zarr label store (`save_dir`)
   roofline       the 16 TMA-fed tcgen05 conv launches (tensor bound), timed live with CUDA events;
@@ -544,7 +544,9 @@ def run_gpu(args, rank, local_rank, world):
     # through `segmentation.segmentation_loop`, the frame loop behind `segment_data` /
     # `affinity_unet_watershed`; with world > 1 every rank runs its own K frames (weak scaling,
     # like `value`) and the label ids are made global by the per-step all-gather
-    n_e2e = max(8 * args.steps, 64)             # long enough that pipeline fill / drain (~1 frame) is amortised
+    # long enough that pipeline fill / drain (~1 frame) is amortised, bounded so that 8 ranks do not
+    # page-lock more than ~50 GB of host memory between them
+    n_e2e = min(max(8 * args.steps, 64), 96)
     series = torch.from_numpy(np.broadcast_to(vol_np, (n_e2e,) + FRAME).copy()).pin_memory()
     out_series = torch.zeros((n_e2e,) + FRAME, dtype=torch.int32).pin_memory()
     config = {'unet': net, 'output_volume': np.zeros((1,), np.float32), 'shard': False,
