@@ -279,6 +279,10 @@ int isg_unet_forward_chunks(isg_unet_plan *plan, const float *frame, float *feat
  * in profiles/r02_notes.md. */
 int isg_unet_forward_chunks_norm(isg_unet_plan *plan, const float *frame, const float *norm_max,
                                  float *feats, void *stream);
+/* host-only query of the band-flat conv tiling for tests: out4 = {P, R, tiles per
+ * plane, plane-slot bytes} for an (H, W) plane, rows of row_bytes, slots of at most max_slot_bytes */
+int isg_debug_flat_tiling(int H, int W, int row_bytes, int64_t max_slot_bytes, int64_t *out4);
+
 /* fp16 range guard.  Filters are divided by a per-output-channel power of two at pack time (the
  * train-mode BatchNorm that follows every convolution cancels it; BN_EPS is rescaled to match), so
  * the fp16 weights and pre-BatchNorm activations stay O(1) for any filter scale.  Should an

@@ -68,6 +68,7 @@ SIGNATURES = {
                                    _vp, _sz]),
     'isg_unet_plan_set_chunks': (_i32, [_vp, _vp, _vp, _vp]),
     'isg_unet_plan_destroy': (None, [_vp]),
+    'isg_debug_flat_tiling': (_i32, [_i32, _i32, _i32, _i64, _vp]),
     'isg_unet_plan_overflowed': (_i32, [_vp]),
     'isg_unet_plan_clear_overflow': (_i32, [_vp, _vp]),
     'isg_unet_forward_chunks': (_i32, [_vp, _vp, _vp, _vp]),

@@ -762,6 +762,22 @@ static int forward(isg_unet_plan *p, const float *frame, float *feats, int stop,
 
 using namespace isg;
 
+// Geometry of the band-flat tiling for an (H, W) plane with rows of `row_bytes` and plane slots of at most
+// `max_slot_bytes` (host only, no device needed: the CPU tests check that every output voxel lies in
+// exactly one tile and that no tap leaves the plane slot).  out4 = {P, R, tiles per plane, slot bytes}.
+extern "C" int isg_debug_flat_tiling(int H, int W, int row_bytes, int64_t max_slot_bytes, int64_t *out4) {
+    ISG_REQUIRE(out4 && H > 0 && W > 0 && row_bytes > 0, ISG_ERR_ARG, "isg_debug_flat_tiling: bad argument");
+    int P = 0, R = 0;
+    long tiles = 0;
+    if (!isg::choose_flat(H, W, row_bytes, (long)max_slot_bytes, P, R, tiles)) {
+        isg::set_error("isg_debug_flat_tiling: no band fits %lld bytes", (long long)max_slot_bytes);
+        return ISG_ERR_ARG;
+    }
+    out4[0] = P; out4[1] = R; out4[2] = tiles;
+    out4[3] = (((int64_t)R * P * row_bytes) + 1023) & ~(int64_t)1023;
+    return ISG_OK;
+}
+
 extern "C" size_t isg_unet_packed_weight_bytes(void) { return pack_layout().total; }
 
 extern "C" int isg_unet_weights_pack(const void *const *tensors, int n_tensors, void *packed, void *stream) {

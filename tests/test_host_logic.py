@@ -276,3 +276,39 @@ def test_label_store_partial_writes_in_place(tmp_path):
         assert np.array_equal(a[11], ref[11]) and np.array_equal(a[5:7, 1:3], ref[5:7, 1:3])
         b = _io.open_zarr(str(tmp_path / f'a{k}'))                    # re-open: own metadata
         assert np.array_equal(np.asarray(b), ref)
+
+
+def test_band_flat_conv_tiling_covers_every_voxel_once():
+    """The band-flat tiling of conv3d_tc (host-side planner, no device needed): a tile is
+    128 consecutive positions f = y*P + x' of a column band.  For many plane sizes: every output
+    voxel lies in exactly one (band, tile, row), and every tap of every row stays inside the R*P rows
+    of the plane slot whose TMA box starts at padded row y0 = 128*fb // P."""
+    import ctypes
+    from iterseg_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 4)()
+    sizes = [(256, 256), (129, 129), (65, 65), (33, 33), (17, 17), (9, 9), (5, 5), (3, 3), (96, 160), (33, 40), (2, 7)]
+    for H, W in sizes:
+        for rb, cap in ((64, 32 << 10), (128, 32 << 10), (128, 24 << 10), (64, 20 << 10)):
+            rc = lib.isg_debug_flat_tiling(H, W, rb, cap, out)
+            if rc != 0:
+                continue
+            P, R, tiles, slot = (int(v) for v in out)
+            Wt = P - 2
+            bands = -(-W // Wt)
+            per_band = -(-(H * P) // 128)
+            assert tiles == bands * per_band and slot >= R * P * rb and slot <= cap
+            f = np.arange(per_band * 128)
+            y, xx = f // P, f % P
+            cover = np.zeros((H, W), int)
+            for wb in range(bands):
+                x = wb * Wt + xx
+                valid = (xx < Wt) & (y < H) & (x < W)
+                np.add.at(cover, (y[valid], x[valid]), 1)
+            assert (cover == 1).all(), (H, W, P)
+            fb = np.arange(per_band)
+            start = (fb * 128) % P                                  # first position inside the slot
+            assert (start + 127 + 2 * P + 2 < R * P).all(), (H, W, P, R)
+            y0 = (fb * 128) // P                                    # slot = padded rows y0 .. y0 + R - 1
+            last_row_needed = (fb * 128 + 127 + 2 * P + 2) // P
+            assert (last_row_needed <= y0 + R - 1).all()
