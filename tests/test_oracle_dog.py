@@ -64,3 +64,22 @@ def test_dog_oracle_runs_and_labels_every_marker():
     assert set(np.unique(out[info['markers'] > 0])) == set(range(1, n + 1))
     assert not out[~(info['mask'] | (info['markers'] > 0))].any()
     assert np.array_equal(info['d2'], np.rint(ndi.distance_transform_edt(np.pad(vol, 1)) ** 2).astype(np.int64))
+
+
+def test_dog_params_multi_layer_match_the_restatement():
+    """The host side of multi-layer blob_dog (no device): sigma list, Gaussian radii and weights handed to the
+    C-ABI are those of the scipy restatement (scikit-image: sigma_list = min_sigma * 1.6**i, truncate 4)."""
+    from iterseg_b200 import segmentation, watershed as ws
+    from oracle import dog
+    for mn, mx in ((1.0, 1.5), (1.0, 2.0), (1.0, 3.0), (0.8, 4.0)):
+        p = segmentation._dog_params(mn, mx, 0.02)
+        sl = dog.sigma_list(mn, mx)
+        assert p.n_layers == len(sl) - 1
+        if p.n_layers > 1:
+            assert [p.layer_sigma[i] for i in range(len(sl))] == sl
+            for i, s in enumerate(sl):
+                w, r = ws.gaussian_half_kernel(s)
+                assert p.layer_radius[i] == r == int(4.0 * s + 0.5)
+                assert [p.layer_weights[i][j] for j in range(r + 1)] == [float(x) for x in w]
+            assert p.mask_radius[1] == int(4.0 * mx + 0.5)
+        assert abs(p.scale_factor - 1.0 / 0.6) < 1e-6 and p.overlap == 0.5
