@@ -41,7 +41,10 @@ struct ZringGeom {
 static constexpr int ZR_P = 32, ZR_HT = 4, ZR_WT = 30;
 static constexpr int ZR_PLANE_ROWS = (ZR_HT + 2) * ZR_P;              // 192
 static constexpr int ZR_PLANE_BYTES = ZR_PLANE_ROWS * 64;             // 12288
-static constexpr int ZR_SLOTS = 4;                                    // plane slots per CTA
+#ifndef ISG_ZR_SLOTS
+#define ISG_ZR_SLOTS 4
+#endif
+static constexpr int ZR_SLOTS = ISG_ZR_SLOTS;                         // plane slots per CTA (TMA prefetch depth)
 static constexpr int ZR_NA = 3;                                       // accumulators in the ring: 3 x 80 columns ->
                                                                       // 256 TMEM columns, TWO CTAs per SM (they fill
                                                                       // each other's MMA -> epilogue bubbles)
