@@ -312,3 +312,57 @@ def test_band_flat_conv_tiling_covers_every_voxel_once():
             y0 = (fb * 128) // P                                    # slot = padded rows y0 .. y0 + R - 1
             last_row_needed = (fb * 128 + 127 + 2 * P + 2) // P
             assert (last_row_needed <= y0 + R - 1).all()
+
+
+LOOP_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch.distributed as dist
+from iterseg_b200 import _io, segmentation
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+T, shape = 7, (4, 8, 6)
+data = np.stack([np.full(shape, t + 1, np.float32) for t in range(T)])
+data[:, 0, 0, 0] = 8.0                                   # the frame maximum: vol /= max leaves (t + 1) / 8
+store = _io.open_zarr(%(store)r, shape=(T,) + shape, chunks=(4, 4, 8), dtype=np.int32)
+if rank == 0:
+    store[3, ...] = np.full(shape, 99, np.int32)          # already segmented: warm restart must skip it
+dist.barrier()
+calls = []
+
+def fake_segmenter(input_volume, current_output, chunk_size, margin, **config):
+    """A plug-in processing function (segmentation.py:898-899 protocol): label = 8 * normalised value."""
+    calls.append(float(input_volume[1, 1, 1]))
+    current_output[1:-1, 1:-1, 1:-1] = np.rint(input_volume * 8).astype(np.uint32)
+
+done = list(segmentation.segmentation_loop(None, data, (4, 4, 8), (0, 0, 0), store, fake_segmenter, {}))
+mine = [t for t in range(rank, T, world) if t != 3]
+assert done == mine, (rank, done, mine)
+assert len(calls) == len(mine)
+dist.barrier()
+a = np.asarray(_io.open_zarr(%(store)r))
+for t in range(T):
+    want = 99 if t == 3 else t + 1
+    assert (a[t].ravel()[1:] == want).all(), (t, a[t].ravel()[:4])
+# opting out: every rank runs the whole series
+out = np.zeros((T,) + shape, np.int32)
+done = list(segmentation.segmentation_loop(None, data, (4, 4, 8), (0, 0, 0), out, fake_segmenter, {'shard': False}))
+assert done == list(range(T))
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write('rank ' + str(rank) + ' ok\n')
+sys.stdout.flush()
+'''
+
+
+def test_segmentation_loop_shards_frames_over_two_ranks_gloo(tmp_path):
+    """The public frame loop under torch.distributed (gloo, world size 2, CPU) with a plug-in processing
+    function of the reference's protocol: frames t = rank (mod 2), warm restart honoured, both ranks
+    writing one store, `shard: False` opting out (segmentation.py:833-882)."""
+    script = tmp_path / 'worker3.py'
+    script.write_text(LOOP_WORKER % {'root': ROOT, 'store': str(tmp_path / 'lab')})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29615', str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
