@@ -377,6 +377,14 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     // pass 0: weights resident -> tile-major issue order, where ONE set of T accumulators already
     //         works as a ring (tile t's epilogue overlaps tiles t+1..), so T can use all of TMEM;
     // pass 1: streamed weights -> weight-stationary order, two accumulator sets.
+    int force_g = 0;                                    // ISG_CONV_G = "<layer>:<taps per weight stage>,..." (experiments)
+    if (const char *ov = getenv("ISG_CONV_G")) {
+        char key[16];
+        snprintf(key, sizeof key, ",%d:", i);
+        std::string lst = std::string(",") + ov + ",";
+        const size_t at = lst.find(key);
+        if (at != std::string::npos) force_g = atoi(lst.c_str() + at + strlen(key));
+    }
     auto place = [&](bool allow_flat, long slot_cap) -> bool {
         bool placed = false;
         for (int pass = 0; pass < 2 && !placed; ++pass) {
@@ -415,6 +423,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
                     } else if (pass == 1 && (!fold || T >= 2)) {
                         for (int G : {9, 3, 1}) {
                             if (fold && G == 1) continue;
+                            if (force_g && G != force_g) continue;
                             const long sb = (long)G * tap_bytes;
                             if (sb > 36 * 1024 && G > 1) continue;
                             long nb = avail / sb;
