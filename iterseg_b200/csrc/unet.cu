@@ -377,6 +377,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     // pass 0: weights resident -> tile-major issue order, where ONE set of T accumulators already
     //         works as a ring (tile t's epilogue overlaps tiles t+1..), so T can use all of TMEM;
     // pass 1: streamed weights -> weight-stationary order, two accumulator sets.
+    long stage_cap = (getenv("ISG_CONV_STAGE_KB") ? atol(getenv("ISG_CONV_STAGE_KB")) : 36) * 1024;
     int force_g = 0;                                    // ISG_CONV_G = "<layer>:<taps per weight stage>,..." (experiments)
     if (const char *ov = getenv("ISG_CONV_G")) {
         char key[16];
@@ -425,7 +426,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
                             if (fold && G == 1) continue;
                             if (force_g && G != force_g) continue;
                             const long sb = (long)G * tap_bytes;
-                            if (sb > 36 * 1024 && G > 1) continue;
+                            if (sb > stage_cap && G > 1) continue;
                             long nb = avail / sb;
                             if (nb < 2) continue;
                             if (nb > 6) nb = 6;
@@ -469,6 +470,24 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
         if (!took) {
             g = rect;
             t.fold = rect_fold;
+        }
+    }
+    // More taps per weight stage are worth more than more stages (every stage boundary is a barrier
+    // wait + commit per tile of the group: c1.conv1 G = 9 / 3 / 1 -> 1.30 / 1.61 / 2.92 ms): when the tiling just
+    // chosen leaves room for two 9-tap stages of up to 80 KB, take them -- but never at the price of the
+    // tiling, the planes per group or the accumulator sets (c5_0.conv0 1.11 -> 1.04 ms; for c2.* the bigger
+    // stages would push out the flat tiles, which are worth more).
+    if (placed && !g.b_resident && g.taps_per_b < 9 && getenv("ISG_CONV_STAGE_KB") == nullptr) {
+        const ConvGeom prev = g;
+        const int prev_fold = t.fold;
+        stage_cap = 80 * 1024;
+        const bool ok2 = place(prev.flat != 0, (long)prev.plane_bytes) && g.flat == prev.flat && g.P == prev.P &&
+                         g.Ht == prev.Ht && g.T == prev.T && g.nsets == prev.nsets && t.fold == prev_fold &&
+                         !g.b_resident && g.taps_per_b > prev.taps_per_b && g.n_b_stages >= 2;
+        stage_cap = 36 * 1024;
+        if (!ok2) {
+            g = prev;
+            t.fold = prev_fold;
         }
     }
     if (!placed) {
