@@ -240,7 +240,7 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
-TC_KERNEL_LABEL = ('conv3d_tc_kernel x13 + conv3d_zring32_kernel x2 + conv3d_zring_kernel '
+TC_KERNEL_LABEL = ('conv3d_tc_kernel x13 + conv3d_zslide32_kernel x2 + conv3d_zring_kernel '
                    '(the 16 TMA-fed tcgen05 implicit-GEMM launches per step)')
 
 

@@ -153,6 +153,28 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
         : "memory");
 }
 
+// zero 32 lanes x 32 (16) consecutive columns
+__device__ __forceinline__ void tmem_st_zero_32x32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_zero_32x16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (ignored for swizzled
 //   K-major, 1) | [32,46) stride byte offset >> 4 (8 rows) | [46,48) version = 1 |

@@ -330,14 +330,22 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
                make_w_map_zring(&t.tmB, p->packed + p->L.w[i], cin);
     }
     // Channel block of the K loop (= shared-memory row: 64 channels -> 128-byte swizzle, 32 -> 64-byte).
-    // Measured per layer on B200 (profiles/r02_notes.md): 32-channel blocks win for the plain layers
-    // with Cout <= 128 (half-size plane slots leave room for G = 3 / 9 taps per weight stage and for
-    // band-flat tiles: c2.conv1 1.15 -> 1.00 ms, c5_0.conv0 1.24 -> 1.11, c6_0.conv0 1.34 -> 1.21, c1.conv1
-    // 1.43 -> 1.31), 64-channel blocks for Cout = 256 (c3.conv1 1.06 vs 1.28 ms) and for the dx-fold layer
-    // (c7_0.conv0 1.31 vs 1.75 ms).  ISG_CONV_CBLK = "<layer index>:<32|64>,..." overrides (diagnosis).
+    // What decides (measured per layer on B200, profiles/r02_notes.md): the MMAs issued back to back into ONE
+    // accumulator -- taps per weight stage x K steps per block -- because every change of the D tile costs the
+    // tensor pipe ~150-300 clocks (the accumulator is written back and the next one fetched), and the room the
+    // plane slots leave for weight stages:
+    //   Cout <= 64 : 32-channel blocks, 9 taps per stage (18 MMAs per visit; 64-channel blocks lose the flat tiles
+    //                and planes per group: c1.conv1 1.43 -> 1.31 ms);
+    //   Cout = 128 : 64-channel blocks, 3 taps per 48 KB stage (12 MMAs per visit; c2.conv1 1.00 -> 0.98 ms,
+    //                c5_0.conv0 1.02 -> 1.00 against 32-channel blocks with 9 taps per stage) -- with at least two
+    //                blocks: c2.conv0 (Cin = 64) keeps 32-channel blocks and its flat tiles (0.60 vs 0.615 ms);
+    //   Cout = 256 : 32-channel blocks, 3 taps per 48 KB stage (6 MMAs per visit instead of 4 with one 64-channel
+    //                tap: c3.conv1 1.09 -> 1.06 ms, c4.* 0.45 -> 0.43);
+    //   dx-fold    : 64-channel blocks (c7_0.conv0 1.31 vs 1.75 ms).
+    // ISG_CONV_CBLK = "<layer index>:<32|64>,..." overrides (diagnosis).
     int cblk = (c0 % 64 == 0 && (c1 % 64 == 0)) ? 64 : 32;
     const bool fold_layer = cout_pad(i) <= 32 && p->W[l] >= 100;
-    if (cout_pad(i) <= 128 && !fold_layer) cblk = 32;
+    if (!fold_layer && (cout_pad(i) <= 64 || cout_pad(i) > 128 || cin < 128)) cblk = 32;
     if (const char *ov = getenv("ISG_CONV_CBLK")) {
         char key[16];
         snprintf(key, sizeof key, ",%d:", i);
@@ -365,7 +373,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     //             stream from L2 halved.
     // Per candidate: T output planes per group = as many accumulators as the set holds, balanced
     // over the z extent; then the weight ring: everything resident if it fits, else G taps per
-    // stage (a stage <= 36 KB) and as many stages as fit (>= 2).
+    // stage (a stage <= 48 KB) and as many stages as fit (>= 2).
     // fold pays for Cout = 32 only: with Cout = 64 the plain kernel (N = 64 at ~48 clk per MMA, a plain
     // epilogue) beats the fold's N = 192 with its three TMEM reads and 64 shuffles per 32 columns
     // (c1.conv0: 1.15 -> 0.74 ms, profiles/r02_notes.md)
@@ -377,7 +385,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
     // pass 0: weights resident -> tile-major issue order, where ONE set of T accumulators already
     //         works as a ring (tile t's epilogue overlaps tiles t+1..), so T can use all of TMEM;
     // pass 1: streamed weights -> weight-stationary order, two accumulator sets.
-    long stage_cap = (getenv("ISG_CONV_STAGE_KB") ? atol(getenv("ISG_CONV_STAGE_KB")) : 36) * 1024;
+    long stage_cap = (getenv("ISG_CONV_STAGE_KB") ? atol(getenv("ISG_CONV_STAGE_KB")) : 48) * 1024;
     int force_g = 0;                                    // ISG_CONV_G = "<layer>:<taps per weight stage>,..." (experiments)
     if (const char *ov = getenv("ISG_CONV_G")) {
         char key[16];
@@ -484,7 +492,7 @@ static bool setup_tc_layer(isg_unet_plan *p, int i, const __half *src0, int c0, 
         const bool ok2 = place(prev.flat != 0, (long)prev.plane_bytes) && g.flat == prev.flat && g.P == prev.P &&
                          g.Ht == prev.Ht && g.T == prev.T && g.nsets == prev.nsets && t.fold == prev_fold &&
                          !g.b_resident && g.taps_per_b > prev.taps_per_b && g.n_b_stages >= 2;
-        stage_cap = 36 * 1024;
+        stage_cap = 48 * 1024;
         if (!ok2) {
             g = prev;
             t.fold = prev_fold;
@@ -560,11 +568,25 @@ static int launch_tc_inst(const TcLayer &t, cudaStream_t st) {
 
 static int launch_tc(const TcLayer &t, cudaStream_t st) {
     if (t.zring == 2) {
-        ISG_CUDA(cudaFuncSetAttribute(conv3d_zring32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
         int grid = t.grid;
         const int avail = num_sms() - post_sms();
         if (grid > avail) grid = avail;
-        conv3d_zring32_kernel<<<grid, Z32_THREADS, t.smem, st>>>(t.tmA0, t.tmB, t.z32);
+        // ISG_Z32_MODE=ring: the round-1 kernel (three accumulators read per output plane); ISG_Z32_EPI=4|8 epilogue warps
+        static const bool ring = getenv("ISG_Z32_MODE") != nullptr && strcmp(getenv("ISG_Z32_MODE"), "ring") == 0;
+        static const int epi = getenv("ISG_Z32_EPI") ? atoi(getenv("ISG_Z32_EPI")) : 8;
+#define ISG_Z32_LAUNCH(KERNEL, EPI)                                                                              \
+    do {                                                                                                         \
+        ISG_CUDA(cudaFuncSetAttribute(KERNEL<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));   \
+        KERNEL<EPI><<<grid, 128 + 32 * EPI, t.smem, st>>>(t.tmA0, t.tmB, t.z32);                                 \
+    } while (0)
+        if (ring || t.z32.D > ZS_NB) {                      // one 32-column TMEM block per output plane of a column
+            if (epi == 8) ISG_Z32_LAUNCH(conv3d_zring32_kernel, 8);
+            else ISG_Z32_LAUNCH(conv3d_zring32_kernel, 4);
+        } else {
+            if (epi == 8) ISG_Z32_LAUNCH(conv3d_zslide32_kernel, 8);
+            else ISG_Z32_LAUNCH(conv3d_zslide32_kernel, 4);
+        }
+#undef ISG_Z32_LAUNCH
         ISG_LAUNCHED();
         return ISG_OK;
     }

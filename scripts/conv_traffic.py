@@ -34,7 +34,7 @@ def val(r, name, scale_to=None):
 layers = []
 for r in data:
     name = r[col['Kernel Name']]
-    if 'conv3d_tc' not in name and 'conv3d_zring' not in name:      # conv3d_zring32 matches too
+    if 'conv3d_tc' not in name and 'conv3d_zring' not in name and 'conv3d_zslide' not in name:      # conv3d_zring32 matches too
         continue
     layers.append({
         'kernel': name[:64],
