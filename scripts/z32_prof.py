@@ -1,7 +1,14 @@
-"""One U-Net forward with the instrumented z-ring kernel (build with ISG_NVCC_EXTRA=-DISG_Z32_PROF): wait-time counters
-of the producer / MMA / epilogue roles of two CTAs, printed by the kernel."""
+"""One U-Net forward with the instrumented round-1 z-ring kernel: wait-time counters of the producer / MMA / epilogue
+roles of two CTAs, printed by the kernel (profiles/r02_notes.md, "what a change of the D tile costs").
+
+    ISG_NVCC_EXTRA=-DISG_Z32_PROF python -m iterseg_b200._build --force
+    ISG_Z32_MODE=ring [ISG_Z32_EPI=4|8] python scripts/z32_prof.py        # on the GPU box
+    python -m iterseg_b200._build --force                                  # back to the shipped library
+"""
 import os
 import sys
+
+os.environ.setdefault('ISG_Z32_MODE', 'ring')     # the counters live in conv3d_zring32_kernel
 
 import torch
 
