@@ -29,8 +29,10 @@ def test_golden_small_chunk(net, golden_dir):
 
 
 # (2,16,16): the smallest valid chunk (one partial tile in x for every kernel); (4,64,16) / (4,16,64):
-# partial tiles in one direction only
-@pytest.mark.parametrize('shape', [(2, 32, 48), (6, 64, 32), (10, 96, 160), (2, 16, 16), (4, 64, 16), (4, 16, 64)])
+# partial tiles in one direction only; (18,32,48): more than 16 planes per z-column, i.e. the 32 -> 32 layers
+# fall back from conv3d_zslide32_kernel (one TMEM block per output plane) to the accumulator-ring kernel
+@pytest.mark.parametrize('shape', [(2, 32, 48), (6, 64, 32), (10, 96, 160), (2, 16, 16), (4, 64, 16), (4, 16, 64),
+                                   (18, 32, 48)])
 def test_odd_shapes_vs_oracle(net, shape):
     from oracle import unet_ref
     x = np.random.default_rng(sum(shape)).random((1, 1) + shape, dtype=np.float32)
